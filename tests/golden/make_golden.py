@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE: (re)generate tests/golden/*.npz from the reference itself.
+
+Runs only where /root/reference and oracle/_ref/ref_dump{12,32} exist (the build
+container). For each scenario it runs the UNMODIFIED reference producer
+(gps.c, gps_thread_ep) behind the recording FIFO of oracle/ref_harness/ref_dump.c
+and stores
+  * the per-block channel parameters the sample loop consumed (f_carr, f_code,
+    code phase, NAV position, gain, carrier phase at block start, NAV words),
+  * CRC-32 digests of every block of the enqueue stream (whole block + 30 parts),
+  * a few verbatim blocks,
+so that the GPU box (which has no /root/reference) can check the CUDA path and the
+C restatement bit for bit against the reference.
+Usage: python tests/golden/make_golden.py [names...]
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refdump  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+LOC = "35.681298,139.766247,10.0"
+START = "2024/01/07,02:00:00"   # = toc of the synthetic ephemerides (avoids date2gps on a zero date)
+
+SCENARIOS = {
+    # name: (nsat, binary, seconds, extra args, keep verbatim blocks)
+    "sky12_static_10s_i8": (12, "ref_dump12", 10, [], [0, 98]),
+    "sky12_static_35s_i8": (12, "ref_dump12", 35, [], []),
+    "sky12_circle_10s_i16": (12, "ref_dump12", 10, ["--iq16", "-m", "/root/reference/circle.csv"], [0]),
+    "sky32_static_10s_i8": (32, "ref_dump32", 10, [], [0]),
+}
+
+
+def run(name):
+    nsat, binary, secs, extra, keep = SCENARIOS[name]
+    with tempfile.TemporaryDirectory() as td:
+        nav = os.path.join(td, "sky.nav")
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "gen_rinex.py"),
+                               "--nsat", str(nsat), "--out", nav])
+        iq, par = os.path.join(td, "iq.bin"), os.path.join(td, "p.bin")
+        subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOC, "-d", str(secs),
+                               "-s", START, "--iq", iq, "--params", par] + extra,
+                              stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+        p = refdump.read_params(par)
+        dt = np.int16 if p["sample_size"] == 2 else np.int8
+        stream = np.fromfile(iq, dtype=dt)
+        ch = p["chans"]
+        nblk = ch.shape[0]
+        assert stream.size == nblk * 600000, (stream.size, nblk)
+        crcs = refdump.block_crcs(stream)
+        blocks = stream.reshape(nblk, 600000)
+        out = dict(
+            max_chan=np.int32(p["max_chan"]), sample_size=np.int32(p["sample_size"]),
+            chans=ch, nav_words=refdump.nav_table(p), crcs=crcs,
+            keep_idx=np.array(keep, np.int32),
+            keep_blocks=np.stack([blocks[i] for i in keep]) if keep else np.zeros((0, 600000), dt),
+            sin512=p["sin512"], cos512=p["cos512"],
+            code_prns=np.array(sorted(p["codes"]), np.int32),
+            codes=np.stack([p["codes"][k] for k in sorted(p["codes"])]),
+        )
+        # NAV words change every 300 blocks: store one copy per distinct frame.
+        nw = out.pop("nav_words")
+        frames, idx = [], np.zeros(nblk, np.int32)
+        for b in range(nblk):
+            if not frames or not np.array_equal(frames[-1], nw[b]):
+                frames.append(nw[b])
+            idx[b] = len(frames) - 1
+        out["nav_frames"] = np.stack(frames)
+        out["nav_frame_of_block"] = idx
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "blocks", nblk, "chan", p["max_chan"], "frames", len(frames),
+              "active", int((ch["prn"][0] > 0).sum()))
+
+
+if __name__ == "__main__":
+    for n in (sys.argv[1:] or SCENARIOS):
+        run(n)
