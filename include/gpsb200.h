@@ -1,0 +1,158 @@
+/* gpsb200 -- B200-native GPS L1 C/A baseband synthesis, C ABI.
+ *
+ * Drop-in for the sample loop of the reference's producer thread
+ * (Mictronics/multi-sdr-gps-sim, gps_thread_ep): everything between the 10 Hz
+ * channel update (gps.c:2731-2765) and fifo_enqueue (gps.c:2860) -- i.e.
+ * gps.c:2767-2857 -- runs as sm_100a CUDA kernels behind these entry points.
+ * Plain C types only; no C++/torch types cross this boundary.
+ *
+ * The second half of this header re-declares, unchanged, the FIFO / sink API of
+ * the reference (fifo.h:19-62, sdr.h:18-39 constants) which libgpsb200.so also
+ * exports (pinned host buffers, fixed tail handling) so that the reference's
+ * consumers (sdr_iqfile.c:22-55, sdr_hackrf.c:236-248, sdr_pluto.c:45-94) work
+ * unmodified against it.
+ */
+#ifndef GPSB200_H
+#define GPSB200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants of the reference (sdr.h:21-34, gps.h:36-57) ------------------ */
+#define GPSB200_SAMPLERATE        3000000           /* TX_SAMPLERATE, sdr.h:21 */
+#define GPSB200_BLOCK_SAMPLES     300000            /* NUM_IQ_SAMPLES, sdr.h:26 */
+#define GPSB200_BLOCK_ELEMS       600000            /* IQ_BUFFER_SIZE, sdr.h:29 (I and Q count separately) */
+#define GPSB200_MAX_CHAN          32                /* reference ships MAX_CHAN 12 (gps.h:36); 32 = all PRNs */
+#define GPSB200_NAV_WORDS         60                /* N_DWRD, gps.h:52 */
+#define GPSB200_CA_LEN            1023              /* CA_SEQ_LEN, gps.h:57 */
+#define GPSB200_SC08              1                 /* gps-sim.h:27 */
+#define GPSB200_SC16              2                 /* gps-sim.h:28 */
+#define GPSB200_HACKRF_BUFFER     262144            /* HACKRF_TRANSFER_BUFFER_SIZE, sdr.h:34 */
+
+/* ---- error codes ------------------------------------------------------------ */
+enum {
+    GPSB200_OK = 0,
+    GPSB200_ERR_ARG = -1,        /* bad argument (NULL, count, sample size, prn, NAV index) */
+    GPSB200_ERR_CUDA = -2,       /* CUDA runtime error; text via gpsb200_last_error() */
+    GPSB200_ERR_RANGE = -3,      /* sum of channel amplitudes would overflow the int16 I/Q the reference stores */
+    GPSB200_ERR_NOMEM = -4
+};
+
+/* One channel for one 0.1 s block: the fields of the reference's channel_t
+ * (gps.h:213-236) and gain[] (gps.c:2300) that the sample loop reads, as left by
+ * computeCodePhase (gps.c:2033-2064) and the gain update (gps.c:2749-2763).
+ * dataBit/codeCA are not passed: they are functions of (iword, ibit, NAV words)
+ * and (code_phase, prn) respectively (gps.c:2059-2060). */
+typedef struct gpsb200_chan {
+    int32_t prn;          /* 1..32; <= 0: channel unused this block (gps.c:2772) */
+    int32_t iword;        /* NAV word index 0..59  (gps.c:2052) */
+    int32_t ibit;         /* bit in word 0..29     (gps.c:2055) */
+    int32_t icode;        /* code period in bit 0..19 (gps.c:2058) */
+    int32_t nav_frame;    /* which NAV frame (set of 60 words) this block uses, see gpsb200_set_nav */
+    int32_t reserved;
+    double f_carr;        /* Hz, Doppler (gps.c:2043) */
+    double f_code;        /* Hz (gps.c:2044) */
+    double carr_phase;    /* cycles in [0,1): used for the first block of a call and whenever prn differs
+                             from the previous block's prn in the same slot (allocateChannel, gps.c:2203-2210);
+                             otherwise the phase is carried from the previous block (gps.c:2821-2826) */
+    double code_phase;    /* chips in [0,1023) (gps.c:2049) */
+    double gain;          /* gps.c:2756 (x2 for Pluto, gps.c:2759-2763) */
+} gpsb200_chan_t;         /* 64 bytes */
+
+typedef struct gpsb200_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t max_chan;          /* 1..32 */
+    int32_t max_blocks;        /* largest nblk of one gpsb200_synth_* call */
+    int32_t max_nav_frames;    /* NAV frames held at once (>= 1) */
+    int32_t host_threads;      /* threads for the exact carrier-phase chain; 0 = auto */
+    int32_t run_samples;       /* device work unit, divides 300000 and is a multiple of 32; 0 = default (2400) */
+} gpsb200_config_t;
+
+typedef struct gpsb200_ctx gpsb200_ctx_t;
+
+/* Per-call statistics (filled when the pointer is not NULL). Times in milliseconds. */
+typedef struct gpsb200_stats {
+    double host_chain_ms;      /* exact carrier chain on the host */
+    double h2d_ms, kernel_ms, d2h_ms;   /* CUDA-event times on the context's stream */
+    double checkpoint_kernel_ms, synth_kernel_ms;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t launches;          /* kernels launched by this call */
+    int32_t reserved;
+} gpsb200_stats_t;
+
+int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out);
+void gpsb200_destroy(gpsb200_ctx_t *ctx);
+const char *gpsb200_last_error(const gpsb200_ctx_t *ctx);
+const char *gpsb200_version(void);
+
+/* NAV words of one channel for one 30 s frame: channel_t.dwrd (gps.h:227) as
+ * built by generateNavMsg (gps.c:2066-2140); only bits 29..0 are used
+ * (gps.c:2812). Copied; may be updated between synth calls. */
+int gpsb200_set_nav(gpsb200_ctx_t *ctx, int frame, int chan, const uint32_t dwrd[GPSB200_NAV_WORDS]);
+
+/* Synthesize nblk consecutive 0.1 s blocks (replaces gps.c:2767-2857 nblk times).
+ *   chans       [nblk][nchan], host memory
+ *   sample_size GPSB200_SC08: dst is int8  I,Q interleaved, iq >> 4 with modulo-256 narrowing (gps.c:2844)
+ *               GPSB200_SC16: dst is int16 I,Q interleaved (gps.c:2842)
+ *   dst         host memory (pinned is faster), nblk * 600000 elements, block after block
+ *   carr_phase_out  optional [nchan]: carrier phase after the last block (what the reference
+ *               leaves in channel_t.carr_phase), to seed the next call
+ * Blocking: returns when dst is complete. */
+int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+                         int sample_size, void *dst, double *carr_phase_out, gpsb200_stats_t *stats);
+
+/* Same, but the output stays in device memory (dst_device: device pointer with room for
+ * nblk * 600000 elements) and the work is only enqueued on `stream` (a cudaStream_t, 0 =
+ * the context's own stream) -- the caller synchronizes. Used for kernel-only timing and
+ * for multi-GPU time-slice sharding where each rank fills its slice of a device buffer. */
+int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+                                int sample_size, void *dst_device, void *stream,
+                                double *carr_phase_out, gpsb200_stats_t *stats);
+
+/* Re-run the device part of the previous gpsb200_synth_blocks_device call (parameters,
+ * carrier chain and checkpoints already resident in HBM): used by bench.py to time the
+ * kernels alone. kernel_mask: 1 = checkpoint kernel, 2 = synthesis kernel, 3 = both. */
+int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream, int kernel_mask);
+
+/* Exact carrier phase after n samples of Doppler f_carr (the chain of gps.c:2821-2826
+ * without stepping every sample); host-only helper, also used by time-slice sharding
+ * to seed a rank's first block. */
+double gpsb200_carrier_advance(double carr_phase, double f_carr, int64_t nsamples);
+
+/* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
+int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
+
+/* ---- FIFO / sink boundary: the reference's own API (fifo.h:19-62) -------------- */
+struct iq_buf {
+    signed char *data8;        /* 8 bit IQ data  */
+    signed short *data16;      /* 16 bit IQ data */
+    unsigned int totalLength;  /* allocated size in elements */
+    unsigned int validLength;  /* valid elements */
+    struct iq_buf *next;
+};
+bool fifo_create(unsigned buffer_count, unsigned buffer_size, unsigned sample_size);
+void fifo_destroy(void);
+void fifo_wait_next(void);
+void fifo_wait_full(void);
+void fifo_halt(void);
+struct iq_buf *fifo_acquire(void);
+void fifo_enqueue(struct iq_buf *buf);
+struct iq_buf *fifo_dequeue(void);
+void fifo_release(struct iq_buf *buf);
+/* gpsb200 extension: reproduce the stock reference's loss of buffers 1..6 of a run
+ * (tail bug, fifo.c:163-168) so that iqdata.bin is byte-identical to the stock program. */
+void fifo_set_compat_drop(bool on);
+
+/* iqfile sink (sdr_iqfile.h:16-18 semantics: writes ./iqdata.bin from the FIFO). */
+int gpsb200_iqfile_start(const char *path, int sample_size);
+void gpsb200_iqfile_stop(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSB200_H */

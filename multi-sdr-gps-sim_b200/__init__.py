@@ -1,0 +1,13 @@
+"""gpsb200: B200-native GPS L1 C/A baseband synthesis (hot path of multi-sdr-gps-sim).
+
+The product is libgpsb200.so (CUDA kernels for sm_100a behind the C ABI of
+include/gpsb200.h). This package is only the host-side convenience layer used by
+the tests and bench.py: ctypes bindings that mirror the C ABI one to one.
+Import it with importlib (the directory name is not a Python identifier):
+
+    gps = importlib.import_module("multi-sdr-gps-sim_b200")
+"""
+from .api import (  # noqa: F401
+    BLOCK_ELEMS, BLOCK_SAMPLES, SC08, SC16, Chan, Config, Context, GpsB200Error, Stats,
+    carrier_advance, codegen, lib, lib_path, CHAN_DTYPE,
+)

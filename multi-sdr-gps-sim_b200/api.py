@@ -1,0 +1,170 @@
+"""ctypes mirror of include/gpsb200.h. No compute happens here and there is no CPU
+fallback: if libgpsb200.so is missing or no CUDA device is present the calls fail."""
+import ctypes as C
+import os
+
+import numpy as np
+
+BLOCK_SAMPLES = 300000
+BLOCK_ELEMS = 600000
+SC08, SC16 = 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libgpsb200.so")
+
+
+class GpsB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gpsb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Chan(C.Structure):
+    """gpsb200_chan_t (64 bytes)."""
+    _fields_ = [("prn", C.c_int32), ("iword", C.c_int32), ("ibit", C.c_int32), ("icode", C.c_int32),
+                ("nav_frame", C.c_int32), ("reserved", C.c_int32),
+                ("f_carr", C.c_double), ("f_code", C.c_double), ("carr_phase", C.c_double),
+                ("code_phase", C.c_double), ("gain", C.c_double)]
+
+
+CHAN_DTYPE = np.dtype([("prn", "<i4"), ("iword", "<i4"), ("ibit", "<i4"), ("icode", "<i4"),
+                       ("nav_frame", "<i4"), ("reserved", "<i4"),
+                       ("f_carr", "<f8"), ("f_code", "<f8"), ("carr_phase", "<f8"),
+                       ("code_phase", "<f8"), ("gain", "<f8")])
+assert CHAN_DTYPE.itemsize == C.sizeof(Chan) == 64
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_chan", C.c_int32), ("max_blocks", C.c_int32),
+                ("max_nav_frames", C.c_int32), ("host_threads", C.c_int32), ("run_samples", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("host_chain_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("checkpoint_kernel_ms", C.c_double), ("synth_kernel_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("launches", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_lib = None
+
+EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
+           "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
+           "gpsb200_carrier_advance", "gpsb200_codegen",
+           "fifo_create", "fifo_destroy", "fifo_wait_next", "fifo_wait_full", "fifo_halt", "fifo_acquire",
+           "fifo_enqueue", "fifo_dequeue", "fifo_release", "fifo_set_compat_drop",
+           "gpsb200_iqfile_start", "gpsb200_iqfile_stop"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path()):
+            raise GpsB200Error(-2, "libgpsb200.so not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(lib_path())
+        L.gpsb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.gpsb200_destroy.argtypes = [C.c_void_p]
+        L.gpsb200_last_error.argtypes = [C.c_void_p]
+        L.gpsb200_last_error.restype = C.c_char_p
+        L.gpsb200_version.restype = C.c_char_p
+        L.gpsb200_set_nav.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.gpsb200_synth_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.POINTER(Stats)]
+        L.gpsb200_synth_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        L.gpsb200_replay_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gpsb200_carrier_advance.argtypes = [C.c_double, C.c_double, C.c_int64]
+        L.gpsb200_carrier_advance.restype = C.c_double
+        L.gpsb200_codegen.argtypes = [C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def codegen(prn):
+    ca = np.zeros(1023, np.uint8)
+    rc = lib().gpsb200_codegen(prn, ca.ctypes.data)
+    if rc:
+        raise GpsB200Error(rc, "gpsb200_codegen(%d)" % prn)
+    return ca
+
+
+def carrier_advance(phase, f_carr, nsamples):
+    return lib().gpsb200_carrier_advance(float(phase), float(f_carr), int(nsamples))
+
+
+class Context:
+    """gpsb200_ctx_t. `chans` arguments are numpy arrays of CHAN_DTYPE shaped [nblk, nchan]."""
+
+    def __init__(self, max_chan, max_blocks, device=0, max_nav_frames=1, host_threads=0, run_samples=0):
+        self._h = C.c_void_p()
+        self.cfg = Config(device, max_chan, max_blocks, max_nav_frames, host_threads, run_samples)
+        rc = lib().gpsb200_create(C.byref(self.cfg), C.byref(self._h))
+        if rc:
+            msg = lib().gpsb200_last_error(self._h).decode() if self._h else "gpsb200_create: bad configuration"
+            if self._h:
+                lib().gpsb200_destroy(self._h)
+                self._h = C.c_void_p()
+            raise GpsB200Error(rc, msg)
+
+    def close(self):
+        if self._h:
+            lib().gpsb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise GpsB200Error(rc, lib().gpsb200_last_error(self._h).decode())
+
+    def set_nav(self, frame, chan, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        assert w.size == 60
+        self._check(lib().gpsb200_set_nav(self._h, frame, chan, w.ctypes.data))
+
+    def set_nav_frames(self, frames):
+        """frames: uint32[nframes, nchan, 60]."""
+        for f in range(frames.shape[0]):
+            for c in range(frames.shape[1]):
+                self.set_nav(f, c, frames[f, c])
+
+    @staticmethod
+    def _chans(chans):
+        a = np.ascontiguousarray(chans, dtype=CHAN_DTYPE)
+        assert a.ndim == 2
+        return a
+
+    def synth_blocks(self, chans, sample_size=SC08, out=None, want_stats=False):
+        """Host-destination path (H2D params + kernels + D2H result). Returns (iq, carr_phase_out[, Stats])."""
+        a = self._chans(chans)
+        nblk, nchan = a.shape
+        dt = np.int16 if sample_size == SC16 else np.int8
+        if out is None:
+            out = np.empty(nblk * BLOCK_ELEMS, dt)
+        assert out.dtype == dt and out.size >= nblk * BLOCK_ELEMS and out.flags.c_contiguous
+        cp = np.zeros(nchan, np.float64)
+        st = Stats()
+        self._check(lib().gpsb200_synth_blocks(self._h, a.ctypes.data, nblk, nchan, sample_size,
+                                               out.ctypes.data, cp.ctypes.data, C.byref(st)))
+        return (out, cp, st) if want_stats else (out, cp)
+
+    def synth_blocks_device(self, chans, sample_size, dst_ptr, stream=0, want_stats=False):
+        """Device-destination path: dst_ptr is a raw device pointer (e.g. torch tensor .data_ptr())."""
+        a = self._chans(chans)
+        nblk, nchan = a.shape
+        cp = np.zeros(nchan, np.float64)
+        st = Stats()
+        self._check(lib().gpsb200_synth_blocks_device(self._h, a.ctypes.data, nblk, nchan, sample_size,
+                                                      C.c_void_p(dst_ptr), C.c_void_p(stream), cp.ctypes.data,
+                                                      C.byref(st) if want_stats else None))
+        return (cp, st) if want_stats else cp
+
+    def replay_device(self, dst_ptr=0, stream=0, kernel_mask=3):
+        self._check(lib().gpsb200_replay_device(self._h, C.c_void_p(dst_ptr), C.c_void_p(stream), kernel_mask))

@@ -1,0 +1,220 @@
+// The reference's producer/consumer FIFO (fifo.h:19-62, fifo.c) rebuilt behind the
+// same names and semantics, so that gps_thread_ep's acquire/enqueue calls
+// (gps.c:2698,2860-2865) and the sinks' dequeue/release calls (sdr_iqfile.c:38-49,
+// sdr_hackrf.c:236-248, sdr_pluto.c:57-68) link against libgpsb200.so unchanged.
+//
+// Differences, all on purpose:
+//   * buffers are page-locked (cudaHostAlloc) when a CUDA device is present, so the
+//     synthesis result is copied device->host straight into data8/data16;
+//   * fifo_enqueue links at the tail AND advances it (the reference forgets to move
+//     fifo_tail, fifo.c:163-168, which silently drops buffers 1..6 of a run);
+//     fifo_set_compat_drop(true) restores that loss for byte-identical iqdata.bin;
+//   * waits are `while` loops (the reference uses `if`, fifo.c:132-136,178-181).
+#include <cuda_runtime_api.h>
+
+#include <atomic>
+#include <cassert>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "../../include/gpsb200.h"
+
+namespace {
+
+std::mutex g_mu;
+std::condition_variable g_notempty, g_empty, g_free, g_full;
+iq_buf *g_head = nullptr, *g_tail = nullptr, *g_freelist = nullptr;
+bool g_halted = false;
+bool g_compat_drop = false;
+bool g_pinned = false;
+bool g_full_signalled = false;
+
+void *alloc_bytes(size_t n) {
+    void *p = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 &&
+        cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess) {
+        g_pinned = true;
+        memset(p, 0, n);
+        return p;
+    }
+    cudaGetLastError();
+    return calloc(1, n);
+}
+
+void free_bytes(void *p) {
+    if (!p) return;
+    if (g_pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+void free_list(iq_buf *h) {
+    while (h) {
+        iq_buf *n = h->next;
+        free_bytes(h->data8);
+        free_bytes(h->data16);
+        free(h);
+        h = n;
+    }
+}
+
+std::thread g_writer;
+std::atomic<bool> g_writer_exit{false};
+std::string g_path;
+int g_sample_size = GPSB200_SC08;
+
+}  // namespace
+
+extern "C" {
+
+void fifo_set_compat_drop(bool on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_compat_drop = on;
+}
+
+bool fifo_create(unsigned buffer_count, unsigned buffer_size, unsigned sample_size) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_halted = false;
+    g_full_signalled = false;
+    for (unsigned i = 0; i < buffer_count; i++) {
+        iq_buf *b = (iq_buf *) calloc(1, sizeof(iq_buf));
+        if (!b) return false;
+        if (sample_size == sizeof(signed short)) b->data16 = (signed short *) alloc_bytes((size_t) buffer_size * 2);
+        else b->data8 = (signed char *) alloc_bytes((size_t) buffer_size);
+        if (!b->data8 && !b->data16) {
+            free(b);
+            return false;
+        }
+        b->totalLength = buffer_size;
+        b->next = g_freelist;
+        g_freelist = b;
+    }
+    return true;
+}
+
+void fifo_destroy(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    free_list(g_head);
+    free_list(g_freelist);
+    g_head = g_tail = g_freelist = nullptr;
+}
+
+void fifo_wait_next(void) {
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_empty.wait(lk, [] { return !g_head || g_halted; });
+}
+
+void fifo_wait_full(void) {
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_full.wait(lk, [] { return g_full_signalled || g_halted; });
+}
+
+void fifo_halt(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    while (g_head) {
+        iq_buf *b = g_head;
+        g_head = b->next;
+        b->next = g_freelist;
+        g_freelist = b;
+    }
+    g_tail = nullptr;
+    g_halted = true;
+    g_notempty.notify_all();
+    g_empty.notify_all();
+    g_free.notify_all();
+    g_full.notify_all();
+}
+
+struct iq_buf *fifo_acquire(void) {
+    std::unique_lock<std::mutex> lk(g_mu);
+    if (!g_halted && !g_freelist) {
+        g_full_signalled = true;          // every buffer is queued: "full" (fifo.c:132-133)
+        g_full.notify_all();
+    }
+    g_free.wait(lk, [] { return g_freelist || g_halted; });
+    if (g_halted) return nullptr;
+    iq_buf *r = g_freelist;
+    g_freelist = r->next;
+    r->validLength = 0;
+    r->next = nullptr;
+    return r;
+}
+
+void fifo_enqueue(struct iq_buf *buf) {
+    assert(buf->validLength <= buf->totalLength);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_halted) {
+        buf->next = g_freelist;
+        g_freelist = buf;
+        return;
+    }
+    buf->next = nullptr;
+    if (!g_head) {
+        g_head = g_tail = buf;
+        g_notempty.notify_one();
+    } else if (g_compat_drop) {
+        // stock behaviour: overwrite tail->next, never advance the tail; the buffer that
+        // was linked there before is leaked (fifo.c:167)
+        g_tail->next = buf;
+    } else {
+        g_tail->next = buf;
+        g_tail = buf;
+    }
+}
+
+struct iq_buf *fifo_dequeue(void) {
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_notempty.wait(lk, [] { return g_head || g_halted; });
+    if (g_halted) return nullptr;
+    iq_buf *r = g_head;
+    g_head = r->next;
+    r->next = nullptr;
+    if (!g_head) {
+        g_tail = nullptr;
+        g_empty.notify_all();
+    }
+    return r;
+}
+
+void fifo_release(struct iq_buf *buf) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    buf->next = g_freelist;
+    g_freelist = buf;
+    g_free.notify_one();
+}
+
+// ---- iqfile sink (sdr_iqfile.c:22-77): dequeue -> fwrite -> release -------------------
+int gpsb200_iqfile_start(const char *path, int sample_size) {
+    if (g_writer.joinable()) return GPSB200_ERR_ARG;
+    g_path = path ? path : "iqdata.bin";            // sdr_iqfile.c:24
+    g_sample_size = sample_size;
+    FILE *fp = fopen(g_path.c_str(), "wb");
+    if (!fp) return GPSB200_ERR_ARG;
+    g_writer_exit = false;
+    g_writer = std::thread([fp] {
+        while (!g_writer_exit) {
+            iq_buf *iq = fifo_dequeue();
+            if (!iq) break;
+            if (g_sample_size == GPSB200_SC16) fwrite(iq->data16, 2, iq->validLength, fp);
+            else fwrite(iq->data8, 1, iq->validLength, fp);
+            fifo_release(iq);
+        }
+        fclose(fp);
+    });
+    return GPSB200_OK;
+}
+
+void gpsb200_iqfile_stop(void) {
+    if (!g_writer.joinable()) return;
+    fifo_wait_next();              // drain what is queued (the reference drops it, sdr_iqfile.c:66-71)
+    g_writer_exit = true;
+    fifo_halt();
+    g_writer.join();
+}
+
+}  // extern "C"

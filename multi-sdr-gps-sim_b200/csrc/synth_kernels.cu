@@ -1,0 +1,283 @@
+// sm_100a kernels for the GPS L1 C/A sample loop of multi-sdr-gps-sim
+// (reference: gps.c:2767-2857). No tensor cores: the path is a per-sample
+// NCO + table lookup + integer accumulate; the bound is instruction issue and
+// shared-memory wavefronts, the output is 2 (int8) or 4 (int16) bytes per sample.
+//
+// Work decomposition
+//   block  = 0.1 s = 300000 samples (the reference's unit, sdr.h:26)
+//   run    = run_samples consecutive samples of one block (default 2400)
+//   k_checkpoints : one thread per (block, channel) walks both NCOs through the
+//                   block with the exact O(#binade crossings) fast-forward of
+//                   nco_exact.h and stores the state at every run start.
+//   k_synth       : one warp per run (32 channels) or per 2/4 runs (<=16/<=8
+//                   channels). LANE = CHANNEL: every lane steps its channel's two
+//                   FP64 NCOs sample by sample with the reference's own rounding
+//                   (__dadd_rn), looks up the gain-scaled carrier table and the
+//                   chip sign in shared memory, and the warp adds the channels
+//                   with one REDUX.SUM (packed I + Q<<16). Sums are staged in
+//                   shared memory and written out 32 samples at a time as
+//                   coalesced int8/int16 I/Q.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nco_exact.h"
+#include "synth_kernels.h"
+#include "synth_tables.h"
+
+namespace gpsb200 {
+
+__constant__ uint8_t c_quarter_sine[128] = {GPSB200_QUARTER_SINE};
+
+__device__ __forceinline__ int sine512(int k) {
+    k &= 511;
+    const int q = k & 255;
+    const int v = c_quarter_sine[q < 128 ? q : 255 - q];
+    return k < 256 ? v : -v;
+}
+
+// ---------------------------------------------------------------------------------
+// Checkpoint kernel
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
+    // warp = 32 consecutive blocks of one channel: same satellite, similar Doppler,
+    // hence similar iteration counts inside a warp.
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const int c = idx / nblk_pad;
+    const int b = idx - c * nblk_pad;
+    if (c >= a.nchan || b >= a.nblk) return;
+    const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
+    RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
+    double x = p.carr0, y = p.code0;
+    int iword = p.nav0 & 0xFF, ibit = (p.nav0 >> 8) & 0xFF, icode = (p.nav0 >> 16) & 0xFF;
+    for (int r = 0; r < a.nruns; r++) {
+        RunCkpt o;
+        o.x = x;
+        o.y = y;
+        o.nav = (uint32_t) iword | ((uint32_t) ibit << 8) | ((uint32_t) icode << 16);
+        o.pad = 0;
+        ck[(size_t) r * a.nchan] = o;
+        if (p.prn <= 0) continue;
+        int64_t periods = 0, dummy = 0;
+        nco_advance<NCO_CODE>(y, p.c_code, a.run_samples, periods);
+        nav_advance(iword, ibit, icode, periods);
+        nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
+    }
+    if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
+}
+
+// ---------------------------------------------------------------------------------
+// Synthesis kernel
+// ---------------------------------------------------------------------------------
+constexpr int kAtabRows = 513;          // row 512 guards carr_phase == 1.0 (SURVEY hard part 6)
+constexpr int kMaxWarps = 25;
+
+template <int GROUP>
+struct SynthSmem {
+    int32_t atab[kAtabRows][32];                 // [k][lane]: I + (Q << 16), gain-scaled (gps.c:2781-2782)
+    int8_t chips[2][GROUP][kChipStride];         // [dataBit -1/+1 -> 1/0][channel][chip]: dataBit*codeCA
+    uint32_t nav[kNavWords][GROUP];              // NAV words of this block's frame
+    int32_t stage[kMaxWarps][32 * (32 / GROUP)]; // per-warp staging of 32 samples per run
+};
+
+template <int GROUP>
+__device__ __forceinline__ int group_sum(int v) {
+    if (GROUP == 32) {
+        return __reduce_add_sync(0xFFFFFFFFu, v);
+    } else {
+#pragma unroll
+        for (int off = GROUP / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        return v;
+    }
+}
+
+template <int GROUP, bool IQ16>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) k_synth(SynthArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SynthSmem<GROUP> &sm = *reinterpret_cast<SynthSmem<GROUP> *>(smem_raw);
+    constexpr int RPW = 32 / GROUP;               // runs per warp
+
+    const int b = blockIdx.x / a.ctas_per_block;
+    const int g = blockIdx.x - b * a.ctas_per_block;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int ch = lane % GROUP, sub = lane / GROUP;
+    const BlockChanDev *bc = a.bc + (size_t) b * a.nchan;
+
+    // ---- per-CTA tables ----------------------------------------------------------
+    for (int i = tid; i < kAtabRows * 32; i += nthr) {
+        const int k = i >> 5, col = i & 31, c = col % GROUP;
+        int32_t e = 0;
+        if (c < a.nchan && bc[c].prn > 0) {
+            const int kk = k < 512 ? k : 511;
+            const double gain = bc[c].gain;
+            // int product -> double, one rounding by the multiply, truncation toward zero
+            const int ai = __double2int_rz(__dmul_rn((double) sine512(kk + 128), gain));
+            const int aq = __double2int_rz(__dmul_rn((double) sine512(kk), gain));
+            e = ai + aq * 65536;
+        }
+        sm.atab[k][col] = e;
+    }
+    for (int i = tid; i < 2 * GROUP * kChipStride; i += nthr) {
+        const int j = i % kChipStride, c = (i / kChipStride) % GROUP, sel = i / (kChipStride * GROUP);
+        int8_t v = 0;
+        if (c < a.nchan && bc[c].prn > 0) v = a.chips[bc[c].prn * kChipStride + j];
+        (&sm.chips[0][0][0])[i] = sel ? (int8_t) -v : v;
+    }
+    for (int i = tid; i < kNavWords * GROUP; i += nthr) {
+        const int w = i / GROUP, c = i % GROUP;
+        uint32_t v = 0;
+        if (c < a.nchan && bc[c].prn > 0)
+            v = a.nav[((size_t) bc[c].frame * a.nchan + c) * kNavWords + w];
+        sm.nav[w][c] = v;
+    }
+    __syncthreads();
+
+    // ---- this lane's run and channel ------------------------------------------------
+    const int run_first = g * a.runs_per_cta;
+    const int run_last = min(run_first + a.runs_per_cta, a.nruns);
+    const int r = run_first + warp * RPW + sub;
+    const bool run_ok = r < run_last;
+    const bool active = run_ok && ch < a.nchan && bc[ch].prn > 0;
+    if (__ballot_sync(0xFFFFFFFFu, run_ok) == 0) return;
+
+    double x = 0.0, y = 0.0, cc = 0.0, dd = 0.0;
+    int iword = 0, ibit = 0, icode = 0;
+    if (active) {
+        const RunCkpt k0 = a.ck[((size_t) b * a.nruns + r) * a.nchan + ch];
+        x = k0.x;
+        y = k0.y;
+        iword = k0.nav & 0xFF;
+        ibit = (k0.nav >> 8) & 0xFF;
+        icode = (k0.nav >> 16) & 0xFF;
+        cc = bc[ch].c_carr;
+        dd = bc[ch].c_code;
+    }
+    // floor(x*512) and floor(y) come out of the low mantissa word of a round-toward-zero
+    // add of 2^43 / 2^52; the chip-table byte offset rides in the same constant.
+    const double K43 = 8796093022208.0;
+    const double K52 = 4503599627370496.0;
+    const int8_t *chip0 = &sm.chips[0][0][0];
+    auto chip_const = [&](int iw, int ib) -> double {
+        const uint32_t w = sm.nav[iw < kNavWords ? iw : kNavWords - 1][ch];
+        const int bit = (w >> (29 - ib)) & 1;                 // gps.c:2812
+        return K52 + (double) (((bit ? 0 : 1) * GROUP + ch) * kChipStride);
+    };
+    double KY = chip_const(iword, ibit);
+    int32_t *stage = &sm.stage[warp][0];
+    const int32_t *acol = &sm.atab[0][lane];
+
+    const int nchunks = a.run_samples / 32;
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+            const int k = __double2loint(__dadd_rz(x, K43));   // (int) floor(carr_phase*512), gps.c:2775
+            const int j = __double2loint(__dadd_rz(y, KY));    // chip-table offset + (int) code_phase, gps.c:2817
+            const int s = chip0[j];                            // dataBit * codeCA
+            const int e = acol[k * 32];
+            const int sum = group_sum<GROUP>(e * s);           // gps.c:2785-2786 over channels
+            if (ch == 0) stage[sub * 32 + i] = sum;
+            x = __dadd_rn(x, cc);                              // gps.c:2821
+            y = __dadd_rn(y, dd);                              // gps.c:2789
+            const bool wrap = ((unsigned) __double2hiint(x) >= 0x3FF00000u) |
+                              ((unsigned) __double2hiint(y) >= 0x408FF800u);
+            if (__any_sync(0xFFFFFFFFu, wrap)) {
+                if (x >= 1.0) x = __dadd_rn(x, -1.0);          // gps.c:2823-2826
+                else if (x < 0.0) x = __dadd_rn(x, 1.0);
+                if (y >= 1023.0) {                             // gps.c:2791-2813
+                    y = __dadd_rn(y, -1023.0);
+                    if (++icode >= 20) {
+                        icode = 0;
+                        if (++ibit >= 30) {
+                            ibit = 0;
+                            ++iword;
+                        }
+                        KY = chip_const(iword, ibit);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- quantise + pack 32 samples per run (gps.c:2833-2845) --------------------
+        if (run_ok) {
+            const size_t samp0 = (size_t) b * kBlockSamples + (size_t) r * a.run_samples + (size_t) chunk * 32 + ch * RPW;
+            if (ch * RPW < 32) {
+                if (IQ16) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + samp0;
+#pragma unroll
+                    for (int t = 0; t < RPW; t++) {
+                        const int p = stage[sub * 32 + ch * RPW + t];
+                        const int iv = (int) (short) (p & 0xFFFF);
+                        const int qv = (p - iv) >> 16;
+                        o[t] = ((uint32_t) iv & 0xFFFFu) | ((uint32_t) qv << 16);
+                    }
+                } else {
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int t = 0; t < RPW; t++) {
+                        const int p = stage[sub * 32 + ch * RPW + t];
+                        const int iv = (int) (short) (p & 0xFFFF);
+                        const int qv = (p - iv) >> 16;
+                        const uint32_t two = (((uint32_t) (iv >> 4)) & 0xFFu) | ((((uint32_t) (qv >> 4)) & 0xFFu) << 8);
+                        packed |= two << (16 * (t & 1));
+                        if (t & 1) {
+                            reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(a.out) + samp0)[t >> 1] = packed;
+                            packed = 0;
+                        }
+                    }
+                    if (RPW == 1) reinterpret_cast<uint16_t *>(a.out)[samp0] = (uint16_t) packed;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------
+static int group_for(int nchan) { return nchan > 16 ? 32 : (nchan > 8 ? 16 : 8); }
+
+template <int GROUP>
+static cudaError_t launch_synth_t(const SynthArgs &a, cudaStream_t s) {
+    const int rpw = 32 / GROUP;
+    const int warps = (a.runs_per_cta + rpw - 1) / rpw;
+    const size_t smem = sizeof(SynthSmem<GROUP>);
+    const int ctas = a.nblk * a.ctas_per_block;
+    cudaError_t e;
+    if (a.iq16) {
+        e = cudaFuncSetAttribute(k_synth<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        k_synth<GROUP, true><<<ctas, warps * 32, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(k_synth<GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        k_synth<GROUP, false><<<ctas, warps * 32, smem, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(const SynthArgs &a, cudaStream_t s) {
+    switch (group_for(a.nchan)) {
+        case 32: return launch_synth_t<32>(a, s);
+        case 16: return launch_synth_t<16>(a, s);
+        default: return launch_synth_t<8>(a, s);
+    }
+}
+
+void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *smem) {
+    const int grp = group_for(a.nchan), rpw = 32 / grp;
+    *ctas = a.nblk * a.ctas_per_block;
+    *threads = ((a.runs_per_cta + rpw - 1) / rpw) * 32;
+    *smem = grp == 32 ? sizeof(SynthSmem<32>) : (grp == 16 ? sizeof(SynthSmem<16>) : sizeof(SynthSmem<8>));
+}
+
+cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const long total = (long) nblk_pad * a.nchan;
+    const int threads = 128;
+    k_checkpoints<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace gpsb200

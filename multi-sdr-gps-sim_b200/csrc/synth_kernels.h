@@ -1,0 +1,52 @@
+// Device-side data layout and launchers of the GPS L1 C/A synthesis kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpsb200 {
+
+constexpr int kBlockSamples = 300000;   // sdr.h:26
+constexpr int kNavWords = 60;           // gps.h:52
+constexpr int kChipStride = 1024;       // 1023 chips + 1 pad
+
+// One record per (block, channel slot), written by the host, read by both kernels.
+struct BlockChanDev {
+    double c_carr;     // fl(f_carr * delt)  (gps.c:2821)
+    double c_code;     // fl(f_code * delt)  (gps.c:2789)
+    double gain;       // gps.c:2756
+    double carr0;      // exact carrier phase at the first sample of the block
+    double code0;      // code phase at the first sample (computeCodePhase, gps.c:2049)
+    int32_t prn;       // 0 = slot unused
+    uint32_t nav0;     // iword | ibit << 8 | icode << 16 at the first sample
+    int32_t frame;     // NAV frame index
+    int32_t pad[3];
+};
+static_assert(sizeof(BlockChanDev) == 64, "BlockChanDev layout");
+
+// Exact NCO state at the first sample of a run (run = run_samples consecutive samples).
+struct RunCkpt {
+    double x;          // carrier phase
+    double y;          // code phase
+    uint32_t nav;      // iword | ibit << 8 | icode << 16
+    uint32_t pad;
+};
+static_assert(sizeof(RunCkpt) == 24, "RunCkpt layout");
+
+struct SynthArgs {
+    const BlockChanDev *bc;   // [nblk][nchan]
+    RunCkpt *ck;              // [nblk][nruns][nchan]
+    const uint32_t *nav;      // [frames][nchan][60]
+    const int8_t *chips;      // [33][1024]  +1/-1 per chip (codeCA, gps.c:2817), row 0 unused
+    double *carr_end;         // [nblk][nchan] carrier phase after the block (diagnostic / chain check)
+    void *out;                // nblk * 600000 int8 or int16
+    int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
+};
+
+// Run-start checkpoints for every (block, channel): exact walk, O(#binade crossings).
+cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s);
+// The per-sample synthesis (gps.c:2767-2857): lanes = channels, warp-sum over channels.
+cudaError_t launch_synth(const SynthArgs &a, cudaStream_t s);
+// Threads per CTA and dynamic shared memory the synthesis launch will use (for reporting).
+void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *smem);
+
+}  // namespace gpsb200
