@@ -124,6 +124,13 @@ int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream, in
  * to seed a rank's first block. */
 double gpsb200_carrier_advance(double carr_phase, double f_carr, int64_t nsamples);
 
+/* Exact carrier phases after nblk blocks for every channel slot (same chaining rule as
+ * gpsb200_synth_blocks; phase_in == NULL: block 0 takes chans[0][c].carr_phase, else
+ * phase_in[c] continues a previous call). Host only, `threads` worker threads. A rank of a
+ * time-slice sharded run calls this on the blocks BEFORE its slice to seed its first block. */
+int gpsb200_carrier_chain(const gpsb200_chan_t *chans, int nblk, int nchan, const double *phase_in,
+                          double *phase_out, int threads);
+
 /* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
 

@@ -53,7 +53,7 @@ _lib = None
 
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
-           "gpsb200_carrier_advance", "gpsb200_codegen",
+           "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_codegen",
            "fifo_create", "fifo_destroy", "fifo_wait_next", "fifo_wait_full", "fifo_halt", "fifo_acquire",
            "fifo_enqueue", "fifo_dequeue", "fifo_release", "fifo_set_compat_drop",
            "gpsb200_iqfile_start", "gpsb200_iqfile_stop"]
@@ -79,6 +79,7 @@ def lib():
         L.gpsb200_carrier_advance.argtypes = [C.c_double, C.c_double, C.c_int64]
         L.gpsb200_carrier_advance.restype = C.c_double
         L.gpsb200_codegen.argtypes = [C.c_int, C.c_void_p]
+        L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -93,6 +94,19 @@ def codegen(prn):
 
 def carrier_advance(phase, f_carr, nsamples):
     return lib().gpsb200_carrier_advance(float(phase), float(f_carr), int(nsamples))
+
+
+def carrier_chain(chans, phase_in=None, threads=16):
+    """Exact carrier phase of every slot after all blocks of chans[nblk, nchan] (host only)."""
+    a = np.ascontiguousarray(chans, dtype=CHAN_DTYPE)
+    nblk, nchan = a.shape
+    out = np.zeros(nchan, np.float64)
+    pin = None if phase_in is None else np.ascontiguousarray(phase_in, dtype=np.float64)
+    rc = lib().gpsb200_carrier_chain(a.ctypes.data, nblk, nchan, None if pin is None else pin.ctypes.data,
+                                     out.ctypes.data, threads)
+    if rc:
+        raise GpsB200Error(rc, "gpsb200_carrier_chain")
+    return out
 
 
 class Context:

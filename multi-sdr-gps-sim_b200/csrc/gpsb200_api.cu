@@ -45,7 +45,7 @@ struct gpsb200_ctx {
     BlockChanDev *d_bc = nullptr, *h_bc = nullptr;
     RunCkpt *d_ck = nullptr;
     uint32_t *d_nav = nullptr, *h_nav = nullptr;
-    int8_t *d_chips = nullptr;
+    uint32_t *d_chips = nullptr;
     double *d_carr_end = nullptr;
     void *d_out = nullptr;
     size_t out_bytes = 0;
@@ -151,7 +151,7 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.bc = ctx->d_bc + (size_t) blk0 * nchan;
     a.ck = ctx->d_ck + (size_t) blk0 * ctx->nruns * nchan;
     a.nav = ctx->d_nav;
-    a.chips = ctx->d_chips;
+    a.chipbits = ctx->d_chips;
     a.carr_end = ctx->d_carr_end + (size_t) blk0 * nchan;
     a.out = out;
     a.nblk = nblk;
@@ -159,10 +159,10 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.nruns = ctx->nruns;
     a.run_samples = ctx->cfg.run_samples;
     a.iq16 = sample_size == GPSB200_SC16;
-    // lanes per run follow the channel count; a CTA takes up to 25 warps' worth of runs
+    // lanes per run follow the channel count; a CTA takes up to 24 warps' worth of runs
     const int grp = nchan > 16 ? 32 : (nchan > 8 ? 16 : 8);
     const int rpw = 32 / grp;
-    int per_cta = 25 * rpw;
+    int per_cta = 24 * rpw;
     int ctas = (ctx->nruns + per_cta - 1) / per_cta;
     per_cta = (ctx->nruns + ctas - 1) / ctas;
     a.runs_per_cta = per_cta;
@@ -193,6 +193,41 @@ double gpsb200_carrier_advance(double carr_phase, double f_carr, int64_t nsample
     int64_t dummy = 0;
     nco_advance<NCO_CARRIER>(carr_phase, c, nsamples, dummy);
     return carr_phase;
+}
+
+int gpsb200_carrier_chain(const gpsb200_chan_t *chans, int nblk, int nchan, const double *phase_in,
+                          double *phase_out, int threads) {
+    if (!chans || !phase_out || nblk < 0 || nchan < 1) return GPSB200_ERR_ARG;
+    const double delt = 1.0 / (double) GPSB200_SAMPLERATE;
+    auto work = [&](int lo, int hi) {
+        for (int c = lo; c < hi; c++) {
+            int prn = 0;
+            double ph = phase_in ? phase_in[c] : 0.0;
+            for (int b = 0; b < nblk; b++) {
+                const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
+                if (in.prn <= 0) {
+                    prn = 0;
+                    continue;
+                }
+                if ((b == 0 && !phase_in) || in.prn != prn) {
+                    if (!(b == 0 && phase_in)) ph = in.carr_phase;
+                    prn = in.prn;
+                }
+                int64_t dummy = 0;
+                nco_advance<NCO_CARRIER>(ph, in.f_carr * delt, GPSB200_BLOCK_SAMPLES, dummy);
+            }
+            phase_out[c] = prn > 0 ? ph : 0.0;
+        }
+    };
+    threads = std::max(1, std::min(threads, nchan));
+    std::vector<std::thread> th;
+    const int per = (nchan + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const int lo = t * per, hi = std::min(nchan, lo + per);
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto &t : th) t.join();
+    return GPSB200_OK;
 }
 
 int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
@@ -229,15 +264,17 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaMalloc(&ctx->d_nav, navb));
     CU(cudaHostAlloc(&ctx->h_nav, navb, cudaHostAllocDefault));
     memset(ctx->h_nav, 0, navb);
-    // chip sign table: +1/-1 per chip (codeCA = ca*2-1, gps.c:2817), row = prn
-    std::vector<int8_t> chips((size_t) 33 * kChipStride, 0);
+    // packed C/A chips (ca[], gps.c:2817), periodically extended so that any 32-chip window
+    // starting at chip 0..1022 is two consecutive words; row = prn
+    std::vector<uint32_t> chips((size_t) 33 * kChipWords, 0);
     for (int prn = 1; prn <= 32; prn++) {
         uint8_t ca[GPSB200_CA_LEN];
         ca_code(prn, ca);
-        for (int j = 0; j < GPSB200_CA_LEN; j++) chips[(size_t) prn * kChipStride + j] = ca[j] ? 1 : -1;
+        for (int n = 0; n < kChipWords * 32; n++)
+            if (ca[n % GPSB200_CA_LEN]) chips[(size_t) prn * kChipWords + (n >> 5)] |= 1u << (n & 31);
     }
-    CU(cudaMalloc(&ctx->d_chips, chips.size()));
-    CU(cudaMemcpy(ctx->d_chips, chips.data(), chips.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_chips, chips.size() * 4));
+    CU(cudaMemcpy(ctx->d_chips, chips.data(), chips.size() * 4, cudaMemcpyHostToDevice));
     return GPSB200_OK;
 }
 

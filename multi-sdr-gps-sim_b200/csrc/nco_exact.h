@@ -30,6 +30,13 @@ namespace gpsb200 {
 
 enum NcoKind { NCO_CODE = 0, NCO_CARRIER = 1 };
 
+// Largest double below 1.0. The reference's negative-Doppler wrap `carr_phase += 1.0`
+// (gps.c:2825-2826) can round a tiny negative phase to exactly 1.0, after which its table
+// index (int) floor(1.0 * 512) = 512 reads past cosTable512/sinTable512 (gps.c:2775-2782):
+// undefined behaviour, probability ~2^-54/|c| per wrap. This implementation (and the test
+// oracle) clamp that one value to 1 - 2^-53 instead, which keeps the index at 511.
+constexpr double kBelowOne = 0.99999999999999988897769753748434595763683319091796875;
+
 GPSB_HD uint64_t f64_bits(double v) {
 #if defined(__CUDA_ARCH__)
     return (uint64_t) __double_as_longlong(v);
@@ -65,7 +72,10 @@ GPSB_HD void nco_step(double &x, double c, int64_t &periods) {
         }
     } else {
         if (x >= 1.0) x -= 1.0;
-        else if (x < 0.0) x += 1.0;
+        else if (x < 0.0) {
+            x += 1.0;
+            if (x >= 1.0) x = kBelowOne;
+        }
     }
 }
 

@@ -69,13 +69,13 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
 // ---------------------------------------------------------------------------------
 // Synthesis kernel
 // ---------------------------------------------------------------------------------
-constexpr int kAtabRows = 513;          // row 512 guards carr_phase == 1.0 (SURVEY hard part 6)
-constexpr int kMaxWarps = 25;
+constexpr int kAtabRows = 513;          // row 512 is never addressed (carr_phase < 1.0 always), kept as a guard
+constexpr int kMaxWarps = 24;
 
 template <int GROUP>
 struct SynthSmem {
     int32_t atab[kAtabRows][32];                 // [k][lane]: I + (Q << 16), gain-scaled (gps.c:2781-2782)
-    int8_t chips[2][GROUP][kChipStride];         // [dataBit -1/+1 -> 1/0][channel][chip]: dataBit*codeCA
+    uint32_t cabits[kChipWords][GROUP];          // [word][channel]: C/A chips, bit n = ca[n mod 1023], n < 1056
     uint32_t nav[kNavWords][GROUP];              // NAV words of this block's frame
     int32_t stage[kMaxWarps][32 * (32 / GROUP)]; // per-warp staging of 32 samples per run
 };
@@ -92,7 +92,7 @@ __device__ __forceinline__ int group_sum(int v) {
 }
 
 template <int GROUP, bool IQ16>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) k_synth(SynthArgs a) {
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SynthSmem<GROUP> &sm = *reinterpret_cast<SynthSmem<GROUP> *>(smem_raw);
     constexpr int RPW = 32 / GROUP;               // runs per warp
@@ -118,11 +118,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_synth(SynthArgs a) {
         }
         sm.atab[k][col] = e;
     }
-    for (int i = tid; i < 2 * GROUP * kChipStride; i += nthr) {
-        const int j = i % kChipStride, c = (i / kChipStride) % GROUP, sel = i / (kChipStride * GROUP);
-        int8_t v = 0;
-        if (c < a.nchan && bc[c].prn > 0) v = a.chips[bc[c].prn * kChipStride + j];
-        (&sm.chips[0][0][0])[i] = sel ? (int8_t) -v : v;
+    for (int i = tid; i < kChipWords * GROUP; i += nthr) {
+        const int w = i / GROUP, c = i % GROUP;
+        uint32_t v = 0;
+        if (c < a.nchan && bc[c].prn > 0) v = a.chipbits[bc[c].prn * kChipWords + w];
+        sm.cabits[w][c] = v;
     }
     for (int i = tid; i < kNavWords * GROUP; i += nthr) {
         const int w = i / GROUP, c = i % GROUP;
@@ -154,28 +154,37 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_synth(SynthArgs a) {
         dd = bc[ch].c_code;
     }
     // floor(x*512) and floor(y) come out of the low mantissa word of a round-toward-zero
-    // add of 2^43 / 2^52; the chip-table byte offset rides in the same constant.
+    // add of 2^43 / 2^52 (exact: the addend is an integer-valued double).
     const double K43 = 8796093022208.0;
     const double K52 = 4503599627370496.0;
-    const int8_t *chip0 = &sm.chips[0][0][0];
-    auto chip_const = [&](int iw, int ib) -> double {
+    auto nav_bit = [&](int iw, int ib) -> int {
         const uint32_t w = sm.nav[iw < kNavWords ? iw : kNavWords - 1][ch];
-        const int bit = (w >> (29 - ib)) & 1;                 // gps.c:2812
-        return K52 + (double) (((bit ? 0 : 1) * GROUP + ch) * kChipStride);
+        return (w >> (29 - ib)) & 1;                          // gps.c:2812
     };
-    double KY = chip_const(iword, ibit);
+    int dbit = nav_bit(iword, ibit);
     int32_t *stage = &sm.stage[warp][0];
-    const int32_t *acol = &sm.atab[0][lane];
+    // shared-window byte address of this lane's column of the carrier table
+    const uint32_t abase = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][lane]);
+    const uint32_t *ccol = &sm.cabits[0][ch];
 
     const int nchunks = a.run_samples / 32;
     for (int chunk = 0; chunk < nchunks; chunk++) {
+        // Chip window of this lane for the next 32 samples (<= 12 chips): 24 chips starting at
+        // j0 = (int) code_phase, taken from the periodically extended packed code, XORed with the
+        // data bit, and parked at bit 8 so that a right shift by (chip - j0) leaves the
+        // "flip the sign" flag where it toggles k by 256: table[k ^ 256] = -table[k].
+        const int j0 = __double2loint(__dadd_rz(y, K52));
+        const uint32_t lo = ccol[(j0 >> 5) * GROUP], hi = ccol[((j0 >> 5) + 1) * GROUP];
+        uint32_t w8 = (__funnelshift_r(lo, hi, j0 & 31) ^ (dbit ? 0xFFFFFFFFu : 0u)) << 8;
+        double KY = K52 - (double) j0;
 #pragma unroll 8
         for (int i = 0; i < 32; i++) {
             const int k = __double2loint(__dadd_rz(x, K43));   // (int) floor(carr_phase*512), gps.c:2775
-            const int j = __double2loint(__dadd_rz(y, KY));    // chip-table offset + (int) code_phase, gps.c:2817
-            const int s = chip0[j];                            // dataBit * codeCA
-            const int e = acol[k * 32];
-            const int sum = group_sum<GROUP>(e * s);           // gps.c:2785-2786 over channels
+            const int rel = __double2loint(__dadd_rz(y, KY));  // (int) code_phase - j0, gps.c:2817
+            const int kk = k ^ ((w8 >> rel) & 0x100);          // dataBit*codeCA == -1  <=>  k += 256 (mod 512)
+            int e;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(abase + (uint32_t) kk * 128u));
+            const int sum = group_sum<GROUP>(e);               // gps.c:2785-2786 over channels
             if (ch == 0) stage[sub * 32 + i] = sum;
             x = __dadd_rn(x, cc);                              // gps.c:2821
             y = __dadd_rn(y, dd);                              // gps.c:2789
@@ -183,16 +192,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_synth(SynthArgs a) {
                               ((unsigned) __double2hiint(y) >= 0x408FF800u);
             if (__any_sync(0xFFFFFFFFu, wrap)) {
                 if (x >= 1.0) x = __dadd_rn(x, -1.0);          // gps.c:2823-2826
-                else if (x < 0.0) x = __dadd_rn(x, 1.0);
+                else if (x < 0.0) {
+                    x = __dadd_rn(x, 1.0);
+                    if (x >= 1.0) x = kBelowOne;              // see nco_exact.h: the phase never reads 1.0
+                }
                 if (y >= 1023.0) {                             // gps.c:2791-2813
                     y = __dadd_rn(y, -1023.0);
+                    KY = __dadd_rn(KY, 1023.0);                // the window is periodic in 1023 chips
                     if (++icode >= 20) {
                         icode = 0;
                         if (++ibit >= 30) {
                             ibit = 0;
                             ++iword;
                         }
-                        KY = chip_const(iword, ibit);
+                        const int nb = nav_bit(iword, ibit);
+                        if (nb != dbit) w8 = ~w8;
+                        dbit = nb;
                     }
                 }
             }

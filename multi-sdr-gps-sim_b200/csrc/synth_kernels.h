@@ -7,7 +7,7 @@ namespace gpsb200 {
 
 constexpr int kBlockSamples = 300000;   // sdr.h:26
 constexpr int kNavWords = 60;           // gps.h:52
-constexpr int kChipStride = 1024;       // 1023 chips + 1 pad
+constexpr int kChipWords = 33;          // 1023 chips, periodically extended to 33 x 32 bits
 
 // One record per (block, channel slot), written by the host, read by both kernels.
 struct BlockChanDev {
@@ -36,7 +36,7 @@ struct SynthArgs {
     const BlockChanDev *bc;   // [nblk][nchan]
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
-    const int8_t *chips;      // [33][1024]  +1/-1 per chip (codeCA, gps.c:2817), row 0 unused
+    const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
     double *carr_end;         // [nblk][nchan] carrier phase after the block (diagnostic / chain check)
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;

@@ -106,7 +106,13 @@ void oracle_synth_block(oracle_chan_t *ch, int nchan, int nsamp, int16_t *iq16) 
             }
             carr += dcarr;                                       /* gps.c:2821-2826 */
             if (carr >= 1.0) carr -= 1.0;
-            else if (carr < 0.0) carr += 1.0;
+            else if (carr < 0.0) {
+                carr += 1.0;
+                /* The reference can reach carr == 1.0 here (tiny negative + 1.0 rounds up) and
+                 * then indexes its 512-entry tables with 512: undefined behaviour (SURVEY.md
+                 * hard part 6). Oracle and product both clamp to the largest double below 1. */
+                if (carr >= 1.0) carr = 0.99999999999999988897769753748434595763683319091796875;
+            }
         }
         p->carr_phase = carr; p->code_phase = code;
         p->iword = iword; p->ibit = ibit; p->icode = icode;
