@@ -9,13 +9,14 @@ A "step" is one pass of the hot path over one batch of synthetic input: the
 899.7 Msamples) per GPU. With N ranks the stream is N x 300 s long and time-sliced:
 rank r synthesizes blocks [r*2999, (r+1)*2999) (weak scaling, no data-path collective).
 
-  value  : whole-job Msamples/s with the per-block channel parameters (including each
-           block's exact start carrier phase) already resident in HBM; both kernels
-           (run checkpoints + per-sample synthesis) are inside the timed region, output
-           goes to an HBM buffer. CUDA events, max over ranks.
+  value  : whole-job Msamples/s with the per-block channel parameters (and the resolved
+           block-start carrier phases) already resident in HBM; all three kernels (speculative
+           carrier probe, run checkpoints, per-sample synthesis) are inside the timed region,
+           output goes to an HBM buffer. CUDA events, max over ranks.
   e2e    : the same metric through the blocking C-ABI call gpsb200_synth_blocks with HOST
-           buffers: exact carrier chain on the host, H2D of the parameters, both kernels and
-           D2H of the int8 stream into pinned memory all inside the timed region.
+           buffers: start-phase guesses, H2D of the parameters, probe kernel, D2H of the probes,
+           host fix-up scan, H2D of the start phases, checkpoint + synthesis kernels and D2H of
+           the int8 stream into pinned memory are all inside the timed region.
   roofline: k_synth against the measured HBM copy peak; algorithmic bytes = 2 B per complex
            sample (int8 I+Q) written, nothing else counted.
   cpu_baseline / --impl reference: the reference's own producer loop (oracle/_ref/ref_run*,
@@ -238,22 +239,25 @@ def main():
     ctx.synth_blocks_device(chans, ss, out_dev.data_ptr(), stream=sh)
     torch.cuda.synchronize()
     for _ in range(args.warmup):
-        ctx.replay_device(out_dev.data_ptr(), sh, 3)
+        ctx.replay_device(out_dev.data_ptr(), sh, 7)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     t_wall0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
+        ctx.replay_device(out_dev.data_ptr(), sh, 4)      # speculative carrier probe
+        ev[3 * i + 1].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 1)      # run checkpoints (exact NCO fast-forward)
-        ev[2 * i + 1].record(stream)
+        ev[3 * i + 2].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 2)      # per-sample synthesis
-        ev[2 * i + 2].record(stream)
+        ev[3 * i + 3].record(stream)
     barrier()
     t_wall1 = time.time()
-    total_ms = ev[0].elapsed_time(ev[2 * args.steps])
-    ck_ms = sum((ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))) / args.steps
-    syn_ms = sum((ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))) / args.steps
+    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    pr_ms = sum((ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))) / args.steps
+    ck_ms = sum((ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))) / args.steps
+    syn_ms = sum((ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(args.steps))) / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
@@ -301,8 +305,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 NCO / int32 accumulate / %s out" % ("int16" if args.iq16 else "int8"),
             "data": "synthetic", "config": workload_config(nchan, args.iq16, world),
-            "clocks": clocks, "gpu_launches": 2 * args.steps,
-            "kernels": {"k_checkpoints_ms": round(ck_ms, 3), "k_synth_ms": round(syn_ms, 3)},
+            "clocks": clocks, "gpu_launches": 3 * args.steps,
+            "kernels": {"k_probe_ms": round(pr_ms, 3), "k_checkpoints_ms": round(ck_ms, 3),
+                        "k_synth_ms": round(syn_ms, 3)},
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                          "peak_source": peak_src,
@@ -311,6 +316,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(stats.h2d_bytes) * 1, "d2h_bytes_per_step": int(stats.d2h_bytes),
                     "ms_per_step": round(e2e_s * 1e3, 2), "host_chain_ms": round(stats.host_chain_ms, 2),
+                    "chain_fallbacks": int(stats.chain_fallbacks), "kernel_launches_per_step": int(stats.launches),
                     "host_threads": host_threads, "timing": "wall clock around the blocking call, max over ranks",
                     "output_equals_resident_run": same},
             "slice_seed_s": round(t_seed, 3),

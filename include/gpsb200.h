@@ -77,12 +77,12 @@ typedef struct gpsb200_ctx gpsb200_ctx_t;
 
 /* Per-call statistics (filled when the pointer is not NULL). Times in milliseconds. */
 typedef struct gpsb200_stats {
-    double host_chain_ms;      /* exact carrier chain on the host */
-    double h2d_ms, kernel_ms, d2h_ms;   /* CUDA-event times on the context's stream */
-    double checkpoint_kernel_ms, synth_kernel_ms;
+    double host_chain_ms;      /* host share of the carrier chain: start-phase guesses + fix-up scan */
+    double h2d_ms, kernel_ms, d2h_ms;   /* CUDA-event times on the call's stream */
+    double checkpoint_kernel_ms, synth_kernel_ms, probe_kernel_ms;
     int64_t h2d_bytes, d2h_bytes;
     int32_t launches;          /* kernels launched by this call */
-    int32_t reserved;
+    int32_t chain_fallbacks;   /* blocks whose speculative carrier probe was rejected (exact sequential walk used) */
 } gpsb200_stats_t;
 
 int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out);
@@ -107,16 +107,17 @@ int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nb
                          int sample_size, void *dst, double *carr_phase_out, gpsb200_stats_t *stats);
 
 /* Same, but the output stays in device memory (dst_device: device pointer with room for
- * nblk * 600000 elements) and the work is only enqueued on `stream` (a cudaStream_t, 0 =
- * the context's own stream) -- the caller synchronizes. Used for kernel-only timing and
- * for multi-GPU time-slice sharding where each rank fills its slice of a device buffer. */
+ * nblk * 600000 elements) and the synthesis is only ENQUEUED on `stream` (a cudaStream_t,
+ * 0 = the context's own stream) -- the caller synchronizes before reading dst_device. (The
+ * call itself waits once for the small carrier-probe round trip.) Used for kernel-only
+ * timing and for multi-GPU time-slice sharding where each rank fills a device buffer. */
 int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                                 int sample_size, void *dst_device, void *stream,
                                 double *carr_phase_out, gpsb200_stats_t *stats);
 
 /* Re-run the device part of the previous gpsb200_synth_blocks_device call (parameters,
- * carrier chain and checkpoints already resident in HBM): used by bench.py to time the
- * kernels alone. kernel_mask: 1 = checkpoint kernel, 2 = synthesis kernel, 3 = both. */
+ * start phases and guesses already resident in HBM): used by bench.py to time the kernels
+ * alone. kernel_mask bits: 4 = carrier probe, 1 = run checkpoints, 2 = synthesis. */
 int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream, int kernel_mask);
 
 /* Exact carrier phase after n samples of Doppler f_carr (the chain of gps.c:2821-2826
@@ -130,6 +131,13 @@ double gpsb200_carrier_advance(double carr_phase, double f_carr, int64_t nsample
  * time-slice sharded run calls this on the blocks BEFORE its slice to seed its first block. */
 int gpsb200_carrier_chain(const gpsb200_chan_t *chans, int nblk, int nchan, const double *phase_in,
                           double *phase_out, int threads);
+
+/* Host-only view of the parallel-in-time carrier chain (what the device probe kernel plus
+ * the host fix-up do per block): walk `nsamples` from the GUESSED phase, then derive the exact
+ * end phase of the TRUE start phase from it. Returns 1 and *end_out when the speculation is
+ * accepted (then *end_out == gpsb200_carrier_advance(start, ...), bit for bit), 0 when it is
+ * rejected (the pipeline then walks that block sequentially). For tests. */
+int gpsb200_carrier_probe_fixup(double start, double guess, double f_carr, int64_t nsamples, double *end_out);
 
 /* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);

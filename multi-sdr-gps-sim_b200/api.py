@@ -45,15 +45,17 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("host_chain_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("checkpoint_kernel_ms", C.c_double), ("synth_kernel_ms", C.c_double),
+                ("probe_kernel_ms", C.c_double),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("launches", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("chain_fallbacks", C.c_int32)]
 
 
 _lib = None
 
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
-           "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_codegen",
+           "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_probe_fixup",
+           "gpsb200_codegen",
            "fifo_create", "fifo_destroy", "fifo_wait_next", "fifo_wait_full", "fifo_halt", "fifo_acquire",
            "fifo_enqueue", "fifo_dequeue", "fifo_release", "fifo_set_compat_drop",
            "gpsb200_iqfile_start", "gpsb200_iqfile_stop"]
@@ -79,6 +81,7 @@ def lib():
         L.gpsb200_carrier_advance.argtypes = [C.c_double, C.c_double, C.c_int64]
         L.gpsb200_carrier_advance.restype = C.c_double
         L.gpsb200_codegen.argtypes = [C.c_int, C.c_void_p]
+        L.gpsb200_carrier_probe_fixup.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_double)]
         L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -180,5 +183,5 @@ class Context:
                                                       C.byref(st) if want_stats else None))
         return (cp, st) if want_stats else cp
 
-    def replay_device(self, dst_ptr=0, stream=0, kernel_mask=3):
+    def replay_device(self, dst_ptr=0, stream=0, kernel_mask=7):
         self._check(lib().gpsb200_replay_device(self._h, C.c_void_p(dst_ptr), C.c_void_p(stream), kernel_mask))

@@ -57,6 +57,20 @@ GPSB_HD double bits_f64(uint64_t b) {
 #endif
 }
 
+// A k with k <= floor(room / d), never more than one short of it (room, d < 2^53).
+// Any such k is valid for the jump; only the iteration count depends on it. The device
+// version avoids the (slow, ~100-instruction) 64-bit integer division.
+GPSB_HD uint64_t safe_quotient(uint64_t room, uint64_t d) {
+#if defined(__CUDA_ARCH__)
+    // both operands convert exactly; rcp and mul each err by <= 2^-53 relative; shaving
+    // 2^-49 guarantees q <= room/d.
+    const double q = __dmul_rd(__dmul_rd((double) room, __drcp_rd((double) d)), 1.0 - 0x1p-49);
+    return (uint64_t) __double2ull_rd(q);
+#else
+    return room / d;
+#endif
+}
+
 // One step exactly as the reference performs it. `periods` counts code wraps.
 template <int KIND>
 GPSB_HD void nco_step(double &x, double c, int64_t &periods) {
@@ -79,10 +93,11 @@ GPSB_HD void nco_step(double &x, double c, int64_t &periods) {
     }
 }
 
-// Advance x by exactly n reference steps of increment c.
+// Advance x by exactly n reference steps of increment c -- integer-lattice formulation
+// (any c; used for degenerate increments and as the cross-check of the fast version below).
 // Returns the number of loop iterations spent (diagnostics only).
 template <int KIND>
-GPSB_HD int nco_advance(double &x, double c, int64_t n, int64_t &periods) {
+GPSB_HD int nco_advance_generic(double &x, double c, int64_t n, int64_t &periods) {
     const uint64_t MANT = (1ull << 52) - 1;
     int iters = 0;
     if (c == 0.0 || n <= 0) return 0;
@@ -134,7 +149,7 @@ GPSB_HD int nco_advance(double &x, double c, int64_t n, int64_t &periods) {
         } else {
             room = X - (1ull << 52);
         }
-        uint64_t k = room / (Cq + 1);
+        uint64_t k = safe_quotient(room, Cq + 1);
         if (k > (uint64_t) n) k = (uint64_t) n;
         if (k > 0) {
             X = neg ? X - k * R : X + k * R;
@@ -147,6 +162,243 @@ GPSB_HD int nco_advance(double &x, double c, int64_t n, int64_t &periods) {
         }
     }
     return iters;
+}
+
+// ---------------------------------------------------------------------------------
+// Fast formulation of the same walk: all lattice quantities come out of FP64 itself.
+//   * the in-binade step R*u is c rounded to the binade's grid: (2^e + |c|) - 2^e
+//     (round-half-even there == "the even neighbour" on an exact tie);
+//   * the number of steps that provably stay inside is floor(room * rinv), rinv a
+//     slightly shrunk 1/|c| (valid while ulp(x)/|c| <= 2^-30, i.e. |c| >= 2^-23);
+//   * k * (R*u) and x + k*(R*u) are exact in double (k*R < 2^53).
+// Every iteration executes the same instruction sequence (selects, no data-dependent
+// branches besides the loop itself), which keeps the lanes of a GPU warp together.
+struct WalkConst {
+    double c, ac, rinv;
+    int ec;
+    bool neg, fast;
+};
+
+GPSB_HD WalkConst walk_const(double c) {
+    WalkConst w;
+    w.c = c;
+    w.neg = c < 0.0;
+    const uint64_t cb = f64_bits(c) & 0x7FFFFFFFFFFFFFFFull;
+    w.ac = bits_f64(cb);
+    w.ec = (int) (cb >> 52);
+    w.fast = w.ec >= 1023 - 23 && w.ec < 1023 + 9;      // 2^-23 <= |c| < 512
+    w.rinv = w.fast ? (1.0 / w.ac) * (1.0 - 0x1p-29) : 0.0;
+    return w;
+}
+
+// One iteration: jump as far as provably stays inside the current binade, then (if steps
+// remain) one real step. `special` iterations (x below |c|, non-positive x, or an odd
+// mantissa in a tie binade) jump zero steps. Returns true when the real step wrapped.
+template <int KIND>
+GPSB_HD bool walk_iteration(double &x, const WalkConst &w, int64_t &n, int64_t &periods, double *after_jump) {
+    const uint64_t bx = f64_bits(x);
+    const int ex = (int) ((bx >> 52) & 0x7FF);
+    bool special = (bx >> 63) || !(x >= w.ac);
+    const double lo = bits_f64((uint64_t) ex << 52);
+    double stepd = (lo + w.ac) - lo;                    // |c| rounded to the grid of [2^e, 2^(e+1))
+    if (ex == w.ec) stepd = w.ac;                       // own binade of c: steps are exact
+    const double half_u = bits_f64((uint64_t) (ex > 53 ? ex - 53 : 0) << 52);
+    const double res = w.ac - stepd;
+    special |= ((res == half_u) | (res == -half_u)) & ((bx & 1) != 0);
+    double room;
+    if (!w.neg) {
+        const uint64_t top = (KIND == NCO_CODE && ex == 1023 + 9) ? f64_bits(1023.0) : ((uint64_t) (ex + 1) << 52);
+        room = bits_f64(top - 1) - x;                   // distance to the last double inside
+    } else {
+        room = x - lo;
+    }
+    double kq = room * w.rinv;
+    const double nd = (double) n;
+    if (kq > nd) kq = nd;
+    if (special) kq = 0.0;
+    const int32_t k = (int32_t) kq;                     // n <= 2^31 per call
+    const double adv = (double) k * stepd;              // exact
+    x = w.neg ? x - adv : x + adv;                      // exact
+    n -= k;
+    if (after_jump) *after_jump = x;
+    bool wrapped = false;
+    if (n > 0) {
+        const double before = x;
+        nco_step<KIND>(x, w.c, periods);
+        --n;
+        wrapped = w.neg ? (x > before) : (x < before);
+    }
+    return wrapped;
+}
+
+// Advance x by exactly n reference steps of increment c (n < 2^31).
+// Returns the number of loop iterations spent (diagnostics only).
+template <int KIND>
+GPSB_HD int nco_advance(double &x, double c, int64_t n, int64_t &periods) {
+    if (c == 0.0 || n <= 0) return 0;
+    const WalkConst w = walk_const(c);
+    if (!w.fast || (KIND == NCO_CODE && w.neg)) return nco_advance_generic<KIND>(x, c, n, periods);
+    int iters = 0;
+    while (n > 0) {
+        ++iters;
+        walk_iteration<KIND>(x, w, n, periods, nullptr);
+    }
+    return iters;
+}
+
+// ---------------------------------------------------------------------------------
+// Parallel-in-time carrier chain: speculate per block, fix up sequentially.
+//
+// The carrier phase at the start of block b+1 is the end state of block b, a chain
+// that is serial over the whole run. It is broken up with one property of the
+// recurrence: if two trajectories of the SAME block (same c) have both just wrapped at
+// the same sample, they differ by a multiple G of the coarsest rounding grid in play
+// (G = 2^-52 for c > 0: results in [1,2) before the wrap subtraction; G = 2^-53 for
+// c < 0), and from then on every rounding step commutes with that shift -- so the two
+// stay exactly parallel -- as long as (1) they are in the same binade at every step,
+// and (2) the shift is an EVEN multiple of G (an exact round-half-even tie resolves
+// identically only then).
+// carrier_probe() walks a block from a GUESSED start phase and reports: the sample
+// index and state right after its first wrap; then, for both parities v (start state
+// x_w and x_w + G), the end-of-block state and how far the trajectory could be shifted
+// up/down without any visited state leaving its binade. carrier_fixup() (host, serial
+// over blocks, a few jump iterations each) walks the TRUE start phase to that first
+// wrap, picks the parity with an even shift, checks the shift against the margins and
+// returns the exact end state -- or reports failure, in which case the caller falls
+// back to the exact sequential walk nco_advance(). Either way the result is exact.
+struct CarrierProbe {
+    double x_w;          // guessed trajectory right after its first wrap
+    double x_end[2];     // end-of-block state for start x_w + v*G
+    double m_pos[2];     // largest upward shift tolerated (exclusive)
+    double m_neg[2];     // largest downward shift tolerated (inclusive)
+    int32_t n_w;         // steps done when the first wrap happened (1-based), -1: no wrap in the block
+    int32_t pad;
+};
+
+GPSB_HD double carrier_grid(double c) { return c > 0.0 ? 0x1p-52 : 0x1p-53; }
+
+// distance of v to the edges of its own binade [2^e, 2^(e+1)); 0 for v <= 0
+GPSB_HD void binade_margins(double v, double &m_pos, double &m_neg) {
+    const uint64_t b = f64_bits(v);
+    if ((b >> 63) || (b >> 52) == 0) {
+        m_pos = 0.0;
+        m_neg = 0.0;
+        return;
+    }
+    const double lo = bits_f64(b & 0xFFF0000000000000ull);
+    const double up = (lo + lo) - v, dn = v - lo;
+    if (up < m_pos) m_pos = up;
+    if (dn < m_neg) m_neg = dn;
+}
+
+// Walk up to n steps like nco_advance<NCO_CARRIER>; stop right after the first wrap when
+// stop_at_wrap; when margins are requested, fold every explicitly visited state (before the
+// jump, after the jump, after the real step) into them. Returns the number of steps done.
+// Degenerate increments (|c| < 2^-23) are not walked here: ok is cleared and the caller
+// treats the block as "no usable speculation".
+GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, bool &wrapped, bool &ok,
+                             double *m_pos, double *m_neg) {
+    wrapped = false;
+    ok = true;
+    if (n <= 0) return 0;
+    const WalkConst w = walk_const(c);
+    if (c == 0.0 || !w.fast) {
+        ok = false;
+        return 0;
+    }
+    const int64_t n0 = n;
+    int64_t dummy = 0;
+    while (n > 0) {
+        double aj;
+        if (m_pos) binade_margins(x, *m_pos, *m_neg);
+        const bool wr = walk_iteration<NCO_CARRIER>(x, w, n, dummy, &aj);
+        if (m_pos) {
+            binade_margins(aj, *m_pos, *m_neg);
+            binade_margins(x, *m_pos, *m_neg);
+        }
+        if (wr) {
+            wrapped = true;
+            if (stop_at_wrap) break;
+        }
+    }
+    return n0 - n;
+}
+
+GPSB_HD void carrier_probe(double guess, double c, int64_t n, CarrierProbe &o) {
+    double x = guess;
+    bool wrapped = false, ok = true;
+    const int64_t nw = carrier_walk(x, c, n, true, wrapped, ok, nullptr, nullptr);
+    o.pad = 0;
+    if (!wrapped || !ok) {
+        o.n_w = -1;
+        o.x_w = x;
+        o.x_end[0] = o.x_end[1] = x;
+        o.m_pos[0] = o.m_pos[1] = o.m_neg[0] = o.m_neg[1] = 0.0;
+        return;
+    }
+    o.n_w = (int32_t) nw;
+    o.x_w = x;
+    const double G = carrier_grid(c);
+    for (int v = 0; v < 2; v++) {
+        double xv = o.x_w + (v ? G : 0.0);     // exact: x_w is a multiple of G
+        double mp = 1.0, mn = 1.0;
+        bool w2, ok2;
+        // a parity partner that left [0,1) (x_w at the very edge) is simply unusable
+        if (!(xv >= 0.0 && xv < 1.0)) mp = mn = 0.0;
+        else carrier_walk(xv, c, n - nw, false, w2, ok2, &mp, &mn);
+        o.x_end[v] = xv;
+        o.m_pos[v] = mp;
+        o.m_neg[v] = mn;
+    }
+}
+
+// Exact end-of-block carrier phase from the true start s and the probe of a guessed start.
+// Returns false when the speculation cannot be used (caller then runs nco_advance).
+GPSB_HD bool carrier_fixup(double s, double c, const CarrierProbe &p, double &x_end) {
+    if (p.n_w < 0) return false;
+    double a = s;
+    bool wrapped = false, ok = true;
+    // the true trajectory must wrap for the first time exactly at step n_w
+    const int64_t done = carrier_walk(a, c, p.n_w, true, wrapped, ok, nullptr, nullptr);
+    if (!ok || !wrapped || done != p.n_w) return false;
+    const double G = carrier_grid(c);
+    const double d0 = a - p.x_w;                        // exact: both multiples of G, both small
+    const double q = d0 / G;                            // exact scaling by a power of two
+    if (!(q > -0x1p40 && q < 0x1p40)) return false;
+    const long long qi = (long long) q;
+    if ((double) qi != q) return false;
+    const int v = (int) (qi & 1);
+    const double d = d0 - (v ? G : 0.0);                // even multiple of G
+    // half the measured room as a safety factor (margins are ~1e-7, shifts ~1e-12)
+    if (!(d < 0.5 * p.m_pos[v] && -d < 0.5 * p.m_neg[v])) return false;
+    x_end = p.x_end[v] + d;                             // exact: the sum IS the true state
+    return true;
+}
+
+// Expected rounding drift per step of the carrier recurrence (host only): while the phase
+// sweeps [0,1) uniformly it spends a fraction 2^e of the steps in binade [2^e, 2^(e+1)),
+// where each step really adds R_e*u_e instead of c. Used to GUESS block-start phases for
+// carrier_probe(); accuracy only affects how often carrier_fixup() must fall back.
+inline double carrier_drift_per_step(double c) {
+    if (c == 0.0) return 0.0;
+    const uint64_t MANT = (1ull << 52) - 1;
+    const uint64_t cb = f64_bits(c) & 0x7FFFFFFFFFFFFFFFull;
+    const int ec = (int) (cb >> 52);
+    if (ec == 0) return 0.0;
+    const uint64_t cm = (cb & MANT) | (1ull << 52);
+    double tot = 0.0;
+    for (int ex = ec + 1; ex <= 1022; ex++) {           // up to the binade [0.5, 1)
+        const int sh = ex - ec;
+        if (sh >= 53) break;
+        const uint64_t Cq = cm >> sh, rem = cm & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+        double up = 0.0;                                 // R - Cq
+        if (rem > half || (rem == half && (Cq & 1))) up = 1.0;
+        const double frac = (double) rem / (double) (1ull << sh);
+        // weight 2^e times rho_e = (up - frac) * u_e, with e = ex - 1023, u_e = 2^(e-52)
+        const int e = ex - 1023;
+        tot += (up - frac) * bits_f64((uint64_t) (1023 + 2 * e - 52) << 52);
+    }
+    return c > 0.0 ? tot : -tot;
 }
 
 // NAV-message position after `periods` more code periods (gps.c:2793-2812):

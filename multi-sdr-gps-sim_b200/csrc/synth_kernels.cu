@@ -6,9 +6,12 @@
 // Work decomposition
 //   block  = 0.1 s = 300000 samples (the reference's unit, sdr.h:26)
 //   run    = run_samples consecutive samples of one block (default 2400)
-//   k_checkpoints : one thread per (block, channel) walks both NCOs through the
-//                   block with the exact O(#binade crossings) fast-forward of
-//                   nco_exact.h and stores the state at every run start.
+//   k_probe       : one thread per (block, channel) walks the carrier NCO through the
+//                   block from a GUESSED start phase (speculative, parallel in time);
+//                   the host turns the probes into exact start phases (nco_exact.h).
+//   k_checkpoints : two threads per (block, channel) walk the code and the carrier NCO
+//                   through the block with the exact O(#binade crossings) fast-forward
+//                   and store the state at every run start.
 //   k_synth       : one warp per run (32 channels) or per 2/4 runs (<=16/<=8
 //                   channels). LANE = CHANNEL: every lane steps its channel's two
 //                   FP64 NCOs sample by sample with the reference's own rounding
@@ -36,34 +39,69 @@ __device__ __forceinline__ int sine512(int k) {
 }
 
 // ---------------------------------------------------------------------------------
-// Checkpoint kernel
+// Carrier probe and checkpoint kernels
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
-    // warp = 32 consecutive blocks of one channel: same satellite, similar Doppler,
-    // hence similar iteration counts inside a warp.
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// Thread mapping of both: warp = 32 consecutive blocks of ONE channel (same satellite,
+// similar Doppler, hence similar iteration counts across the lanes of a warp).
+__device__ __forceinline__ bool map_block_chan(const SynthArgs &a, int idx, int &b, int &c) {
     const int nblk_pad = (a.nblk + 31) & ~31;
-    const int c = idx / nblk_pad;
-    const int b = idx - c * nblk_pad;
-    if (c >= a.nchan || b >= a.nblk) return;
-    const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
-    RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
-    double x = p.carr0, y = p.code0;
-    int iword = p.nav0 & 0xFF, ibit = (p.nav0 >> 8) & 0xFF, icode = (p.nav0 >> 16) & 0xFF;
-    for (int r = 0; r < a.nruns; r++) {
-        RunCkpt o;
-        o.x = x;
-        o.y = y;
-        o.nav = (uint32_t) iword | ((uint32_t) ibit << 8) | ((uint32_t) icode << 16);
+    c = idx / nblk_pad;
+    b = idx - c * nblk_pad;
+    return c < a.nchan && b < a.nblk;
+}
+
+__global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
+    int b, c;
+    if (!map_block_chan(a, blockIdx.x * blockDim.x + threadIdx.x, b, c)) return;
+    const size_t i = (size_t) b * a.nchan + c;
+    const BlockChanDev p = a.bc[i];
+    CarrierProbe o;
+    if (p.prn > 0) {
+        carrier_probe(a.guess[i], p.c_carr, kBlockSamples, o);
+    } else {
+        o.n_w = -1;
         o.pad = 0;
-        ck[(size_t) r * a.nchan] = o;
-        if (p.prn <= 0) continue;
-        int64_t periods = 0, dummy = 0;
-        nco_advance<NCO_CODE>(y, p.c_code, a.run_samples, periods);
-        nav_advance(iword, ibit, icode, periods);
-        nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
+        o.x_w = 0.0;
+        o.x_end[0] = o.x_end[1] = o.m_pos[0] = o.m_pos[1] = o.m_neg[0] = o.m_neg[1] = 0.0;
     }
-    if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
+    a.probe[i] = o;
+}
+
+__global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
+    // two roles per (block, channel): role 0 walks the code NCO (+ NAV position), role 1 the carrier
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const int per_role = nblk_pad * a.nchan;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int role = idx / per_role;
+    idx -= role * per_role;
+    int b, c;
+    if (role > 1 || !map_block_chan(a, idx, b, c)) return;
+    const size_t i = (size_t) b * a.nchan + c;
+    const BlockChanDev p = a.bc[i];
+    RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
+    if (role == 0) {
+        double y = p.code0;
+        int iword = p.nav0 & 0xFF, ibit = (p.nav0 >> 8) & 0xFF, icode = (p.nav0 >> 16) & 0xFF;
+        for (int r = 0; r < a.nruns; r++) {
+            RunCkpt *o = ck + (size_t) r * a.nchan;
+            o->y = y;
+            o->nav = (uint32_t) iword | ((uint32_t) ibit << 8) | ((uint32_t) icode << 16);
+            o->pad = 0;
+            if (p.prn <= 0) continue;
+            int64_t periods = 0;
+            nco_advance<NCO_CODE>(y, p.c_code, a.run_samples, periods);
+            nav_advance(iword, ibit, icode, periods);
+        }
+    } else {
+        double x = a.carr0[i];
+        for (int r = 0; r < a.nruns; r++) {
+            ck[(size_t) r * a.nchan].x = x;
+            if (p.prn <= 0) continue;
+            int64_t dummy = 0;
+            nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
+        }
+        if (a.carr_end) a.carr_end[i] = x;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -289,9 +327,17 @@ void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *sme
 
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {
     const int nblk_pad = (a.nblk + 31) & ~31;
-    const long total = (long) nblk_pad * a.nchan;
+    const long total = 2L * nblk_pad * a.nchan;
     const int threads = 128;
     k_checkpoints<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s) {
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const long total = (long) nblk_pad * a.nchan;
+    const int threads = 128;
+    k_probe<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ struct BlockChanDev {
     double c_carr;     // fl(f_carr * delt)  (gps.c:2821)
     double c_code;     // fl(f_code * delt)  (gps.c:2789)
     double gain;       // gps.c:2756
-    double carr0;      // exact carrier phase at the first sample of the block
+    double carr0;      // unused by the kernels (start phases travel in SynthArgs::carr0)
     double code0;      // code phase at the first sample (computeCodePhase, gps.c:2049)
     int32_t prn;       // 0 = slot unused
     uint32_t nav0;     // iword | ibit << 8 | icode << 16 at the first sample
@@ -32,8 +32,13 @@ struct RunCkpt {
 };
 static_assert(sizeof(RunCkpt) == 24, "RunCkpt layout");
 
+struct CarrierProbe;          // nco_exact.h
+
 struct SynthArgs {
     const BlockChanDev *bc;   // [nblk][nchan]
+    const double *carr0;      // [nblk][nchan] exact carrier phase at the first sample of each block
+    const double *guess;      // [nblk][nchan] guessed start phases for the speculative probe
+    CarrierProbe *probe;      // [nblk][nchan] probe results
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
@@ -42,6 +47,8 @@ struct SynthArgs {
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
 };
 
+// Speculative carrier walk of every (block, channel) from a guessed start phase (nco_exact.h).
+cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s);
 // Run-start checkpoints for every (block, channel): exact walk, O(#binade crossings).
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s);
 // The per-sample synthesis (gps.c:2767-2857): lanes = channels, warp-sum over channels.

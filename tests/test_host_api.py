@@ -89,6 +89,47 @@ def test_carrier_fast_forward_vs_brute_force_random():
         assert gps.carrier_advance(x, f, n) == y
 
 
+def test_speculative_carrier_probe_is_exact_or_rejected():
+    # parallel-in-time chain: a block walked from a GUESSED start phase plus the host fix-up must
+    # either reproduce the sequential result bit for bit or say "rejected" -- never a wrong phase
+    L = gps.lib()
+    rng = np.random.default_rng(11)
+    accepted = rejected = 0
+    for t in range(3000):
+        s = rng.uniform(0, 1)
+        f = rng.uniform(-5500, 5500) if t % 9 else rng.uniform(-40, 40)
+        err = rng.choice([0.0, 1e-15, 1e-13, 1e-12, 1e-10, 1e-8, 1e-6, 1e-3]) * rng.uniform(-1, 1)
+        g = (s + err) % 1.0
+        out = C.c_double()
+        ok = L.gpsb200_carrier_probe_fixup(s, g, f, 300000, C.byref(out))
+        if ok:
+            accepted += 1
+            assert out.value == gps.carrier_advance(s, f, 300000), (s, g, f)
+        else:
+            rejected += 1
+    assert accepted > 1500 and rejected > 100
+
+
+def test_speculation_accepts_nearly_all_blocks_of_reference_scenarios():
+    # with the drift-model guesses the fix-up should almost never need the sequential fallback
+    g = scenario.load_golden("sky12_static_35s_i8")
+    ch = g["chans"]
+    L = gps.lib()
+    bad = tot = 0
+    for c in range(ch.shape[1]):
+        for b in range(1, ch.shape[0] - 1):
+            s, f = float(ch["carr_phase"][b, c]), float(ch["f_carr"][b, c])
+            guess = (s + 3e-12) % 1.0            # the size of the guess error seen over 35 s
+            out = C.c_double()
+            ok = L.gpsb200_carrier_probe_fixup(s, guess, f, 300000, C.byref(out))
+            tot += 1
+            if ok:
+                assert out.value == float(ch["carr_phase"][b + 1, c])
+            else:
+                bad += 1
+    assert bad <= 0.01 * tot, (bad, tot)
+
+
 def _fifo_run(compat, nblocks=20, nbuf=8, size=1000):
     L = gps.lib()
 
