@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         return (w >> (29 - ib)) & 1;                          // gps.c:2812
     };
     int dbit = nav_bit(iword, ibit);
+    const double cc9 = 9.0 * cc, dd9 = 9.0 * dd;              // conservative 8-step look-ahead (see below)
     int32_t *stage = &sm.stage[warp][0];
     // shared-window byte address of this lane's column of the carrier table
     const uint32_t abase = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][lane]);
@@ -215,37 +216,67 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         const uint32_t lo = ccol[(j0 >> 5) * GROUP], hi = ccol[((j0 >> 5) + 1) * GROUP];
         uint32_t w8 = (__funnelshift_r(lo, hi, j0 & 31) ^ (dbit ? 0xFFFFFFFFu : 0u)) << 8;
         double KY = K52 - (double) j0;
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            const int k = __double2loint(__dadd_rz(x, K43));   // (int) floor(carr_phase*512), gps.c:2775
-            const int rel = __double2loint(__dadd_rz(y, KY));  // (int) code_phase - j0, gps.c:2817
+        // table lookup + channel sum of one sample from a VALID (wrapped) NCO state
+        auto emit = [&](double xs, double ys, int i) {
+            const int k = __double2loint(__dadd_rz(xs, K43));  // (int) floor(carr_phase*512), gps.c:2775
+            const int rel = __double2loint(__dadd_rz(ys, KY)); // (int) code_phase - j0, gps.c:2817
             const int kk = k ^ ((w8 >> rel) & 0x100);          // dataBit*codeCA == -1  <=>  k += 256 (mod 512)
             int e;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(abase + (uint32_t) kk * 128u));
             const int sum = group_sum<GROUP>(e);               // gps.c:2785-2786 over channels
-            if (ch == 0) stage[sub * 32 + i] = sum;
-            x = __dadd_rn(x, cc);                              // gps.c:2821
-            y = __dadd_rn(y, dd);                              // gps.c:2789
-            const bool wrap = ((unsigned) __double2hiint(x) >= 0x3FF00000u) |
-                              ((unsigned) __double2hiint(y) >= 0x408FF800u);
-            if (__any_sync(0xFFFFFFFFu, wrap)) {
-                if (x >= 1.0) x = __dadd_rn(x, -1.0);          // gps.c:2823-2826
-                else if (x < 0.0) {
-                    x = __dadd_rn(x, 1.0);
-                    if (x >= 1.0) x = kBelowOne;              // see nco_exact.h: the phase never reads 1.0
+            stage[sub * 32 + i] = sum;                         // every lane of the group stores the same word
+        };
+        // one reference step with its wrap / NAV-bit bookkeeping (gps.c:2789-2826)
+        auto step_checked = [&](double &xs, double &ys) {
+            xs = __dadd_rn(xs, cc);
+            ys = __dadd_rn(ys, dd);
+            if (xs >= 1.0) xs = __dadd_rn(xs, -1.0);           // gps.c:2823-2826
+            else if (xs < 0.0) {
+                xs = __dadd_rn(xs, 1.0);
+                if (xs >= 1.0) xs = kBelowOne;                // see nco_exact.h: the phase never reads 1.0
+            }
+            if (ys >= 1023.0) {                                // gps.c:2791-2813
+                ys = __dadd_rn(ys, -1023.0);
+                KY = __dadd_rn(KY, 1023.0);                    // the window is periodic in 1023 chips
+                if (++icode >= 20) {
+                    icode = 0;
+                    if (++ibit >= 30) {
+                        ibit = 0;
+                        ++iword;
+                    }
+                    const int nb = nav_bit(iword, ibit);
+                    if (nb != dbit) w8 = ~w8;
+                    dbit = nb;
                 }
-                if (y >= 1023.0) {                             // gps.c:2791-2813
-                    y = __dadd_rn(y, -1023.0);
-                    KY = __dadd_rn(KY, 1023.0);                // the window is periodic in 1023 chips
-                    if (++icode >= 20) {
-                        icode = 0;
-                        if (++ibit >= 30) {
-                            ibit = 0;
-                            ++iword;
-                        }
-                        const int nb = nav_bit(iword, ibit);
-                        if (nb != dbit) w8 = ~w8;
-                        dbit = nb;
+            }
+        };
+        // Samples go in groups of 8. A lane can tell in advance whether one of its NCOs can
+        // wrap within the next 8 steps (both phases move monotonically inside a block, so
+        // "phase + 9 steps is still in range" is a safe test). If no lane of the warp is at
+        // risk the group runs with bare additions (the common case, ~3 in 4 groups); otherwise
+        // every step carries the reference's wrap / NAV-bit bookkeeping.
+#pragma unroll 1
+        for (int g8 = 0; g8 < 32; g8 += 8) {
+            const bool risky = ((unsigned) __double2hiint(__dadd_rn(x, cc9)) >= 0x3FF00000u) |
+                               ((unsigned) __double2hiint(__dadd_rn(y, dd9)) >= 0x408FF800u);
+            if (!__any_sync(0xFFFFFFFFu, risky)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    emit(x, y, g8 + i);
+                    x = __dadd_rn(x, cc);                      // gps.c:2821, no wrap possible
+                    y = __dadd_rn(y, dd);                      // gps.c:2789, no wrap possible
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    emit(x, y, g8 + i);
+                    const double xn = __dadd_rn(x, cc), yn = __dadd_rn(y, dd);
+                    const bool wrap = ((unsigned) __double2hiint(xn) >= 0x3FF00000u) |
+                                      ((unsigned) __double2hiint(yn) >= 0x408FF800u);
+                    if (__any_sync(0xFFFFFFFFu, wrap)) step_checked(x, y);
+                    else {
+                        x = xn;
+                        y = yn;
                     }
                 }
             }
