@@ -219,7 +219,7 @@ def main():
     bytes_per_sample = 4 if args.iq16 else 2
     # this rank's slice of one continuous scenario, seeded with the exact carrier phase at its first block
     chans, nav = gps.synthetic_chans(nblk, nchan, seed=2024, block0=rank * nblk)
-    host_threads = max(1, min(32, (os.cpu_count() or 8) // max(1, world)))
+    host_threads = max(1, min(16, (os.cpu_count() or 8) // max(1, world)))
     t_seed0 = time.time()
     if rank > 0:
         prefix, _ = gps.synthetic_chans(rank * nblk, nchan, seed=2024, block0=0)

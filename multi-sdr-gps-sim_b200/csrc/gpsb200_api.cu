@@ -10,10 +10,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -28,10 +33,79 @@ using namespace gpsb200;
 namespace {
 
 constexpr int kSynthChunk = 256;   // blocks per synthesis launch of the host-destination path (D2H overlap)
+constexpr int kSegFirst = 256;     // first carrier-chain segment of the host-destination path: small, so
+                                   // that the download can start early ...
+constexpr int kSegBlocks = 1024;   // ... later ones larger (their probe kernels are latency bound)
 
 struct ChainState {
     int prn = 0;
     double phase = 0.0;
+};
+
+// Small persistent worker pool: the per-segment host passes are sub-millisecond, so thread
+// creation per pass would dominate them.
+class WorkerPool {
+public:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return (int) th_.size(); }
+    // run job(lo, hi) over [0, n) split into at most size() contiguous ranges; blocks until done
+    void run(int n, const std::function<void(int, int)> &job) {
+        const int parts = std::max(1, std::min(size(), n));
+        if (parts <= 1 || th_.empty()) {
+            job(0, n);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        job_ = &job;
+        n_ = n;
+        parts_ = parts;
+        pending_ = parts;
+        ++epoch_;
+        cv_.notify_all();
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)> *job;
+            int n, parts;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+                job = job_;
+                n = n_;
+                parts = parts_;
+            }
+            if (id < parts) {
+                const int per = (n + parts - 1) / parts, lo = id * per, hi = std::min(n, lo + per);
+                if (lo < hi) (*job)(lo, hi);
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)> *job_ = nullptr;
+    int n_ = 0, parts_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
 };
 
 }  // namespace
@@ -39,7 +113,7 @@ struct ChainState {
 struct gpsb200_ctx {
     gpsb200_config_t cfg{};
     int nruns = 0;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> ev_done;      // one per synthesis chunk
     BlockChanDev *d_bc = nullptr, *h_bc = nullptr;
@@ -53,6 +127,7 @@ struct gpsb200_ctx {
     void *d_out = nullptr;
     size_t out_bytes = 0;
     bool nav_dirty = true;
+    std::unique_ptr<WorkerPool> pool;      // host passes (guesses, fix-up scan)
     SynthArgs last{};                      // replay state
     bool have_last = false;
     std::string err;
@@ -77,22 +152,6 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-template <class F>
-void parallel_channels(int nchan, int nthreads, F &&work) {
-    nthreads = std::max(1, std::min(nthreads, nchan));
-    if (nthreads == 1) {
-        work(0, nchan);
-        return;
-    }
-    std::vector<std::thread> th;
-    const int per = (nchan + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++) {
-        const int lo = t * per, hi = std::min(nchan, lo + per);
-        if (lo < hi) th.emplace_back(work, lo, hi);
-    }
-    for (auto &t : th) t.join();
-}
-
 inline bool is_fresh(const gpsb200_chan_t *chans, int b, int c, int nchan) {
     // block 0 of a call, or a slot whose satellite changed: the caller's carr_phase applies
     return b == 0 || chans[(size_t) (b - 1) * nchan + c].prn != chans[(size_t) b * nchan + c].prn;
@@ -100,13 +159,14 @@ inline bool is_fresh(const gpsb200_chan_t *chans, int b, int c, int nchan) {
 
 // Host pre-pass: validate, fill the device-layout records and GUESS every block's start
 // carrier phase (closed form + expected rounding drift, long double accumulation).
-int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan) {
+int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
+                   const std::vector<ChainState> &chain) {
     const double delt = 1.0 / (double) GPSB200_SAMPLERATE;     // gps.c:2298
     std::vector<int> status(nchan, GPSB200_OK);
-    parallel_channels(nchan, ctx->cfg.host_threads, [&](int c_lo, int c_hi) {
+    ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
-            long double acc = 0.0L;
-            for (int b = 0; b < nblk; b++) {
+            long double acc = chain[c].phase;               // exact phase after block b0-1 (if any)
+            for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
                 BlockChanDev &o = ctx->h_bc[i];
@@ -147,7 +207,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int 
         if (status[c] != GPSB200_OK) return fail(ctx, status[c], "invalid channel parameters in slot " + std::to_string(c));
     // The reference stores (short)i_acc (gps.c:2834); the packed I/Q accumulation is
     // exact as long as |acc| stays inside int16, which bounds the sum of amplitudes.
-    for (int b = 0; b < nblk; b++) {
+    for (int b = b0; b < b1; b++) {
         double amp = 0.0;
         for (int c = 0; c < nchan; c++) amp += std::fabs(ctx->h_bc[(size_t) b * nchan + c].gain) * 250.0;
         if (amp > 32767.0) return fail(ctx, GPSB200_ERR_RANGE, "sum of channel amplitudes exceeds int16 range");
@@ -158,13 +218,13 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int 
 // Host fix-up scan: exact start phase of every block from the probes, serial over blocks
 // per channel, parallel over channels. Returns the number of blocks that needed the
 // sequential fallback walk.
-int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
                       std::vector<ChainState> &chain) {
     std::vector<int64_t> fallbacks(nchan, 0);
-    parallel_channels(nchan, ctx->cfg.host_threads, [&](int c_lo, int c_hi) {
+    ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
-            ChainState st;
-            for (int b = 0; b < nblk; b++) {
+            ChainState st = chain[c];
+            for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
                 ctx->h_carr0[i] = 0.0;
@@ -236,65 +296,86 @@ int check_call(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int ncha
     return GPSB200_OK;
 }
 
-// The whole path for nblk blocks. dst_host != NULL: results are copied to the host chunk by
-// chunk while later chunks are still being synthesized; else they stay at dst_dev.
+// The whole path for nblk blocks. dst_host != NULL: the call is cut into segments; the
+// carrier-chain resolution of a segment (parameters up -> probe -> probes down -> host fix-up
+// -> start phases up -> run checkpoints) runs on its own stream and therefore CONCURRENTLY
+// with the synthesis kernels (the probe/checkpoint kernels are latency bound and fit beside
+// k_synth's CTAs) and the download of earlier segments; results are copied to the host chunk
+// by chunk. Else one segment on the caller's stream, results stay at dst_dev.
 int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
                  void *dst_dev, void *dst_host, cudaStream_t s, double *carr_phase_out, gpsb200_stats_t *stats) {
     gpsb200_stats_t st{};
-    const size_t nbc = (size_t) nblk * nchan;
     const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
-    // 1. host pre-pass
-    double t0 = now_ms();
-    int rc = prepare_blocks(ctx, chans, nblk, nchan);
-    if (rc) return rc;
-    st.host_chain_ms = now_ms() - t0;
-    // 2. parameters up, speculative carrier probe, probes down
-    CU(cudaEventRecord(ctx->ev[0], s));
-    rc = upload_nav(ctx, s);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->d_bc, ctx->h_bc, nbc * sizeof(BlockChanDev), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->d_guess, ctx->h_guess, nbc * sizeof(double), cudaMemcpyHostToDevice, s));
-    CU(cudaEventRecord(ctx->ev[1], s));
-    SynthArgs a{};
-    fill_args(ctx, a, 0, nblk, nchan, sample_size, dst_dev);
-    CU(launch_probe(a, s));
-    CU(cudaEventRecord(ctx->ev[2], s));
-    CU(cudaMemcpyAsync(ctx->h_probe, ctx->d_probe, nbc * sizeof(CarrierProbe), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    // 3. exact block-start phases (host, serial over blocks per channel, cheap)
-    t0 = now_ms();
     std::vector<ChainState> chain(nchan);
-    st.chain_fallbacks = (int32_t) resolve_chain(ctx, chans, nblk, nchan, chain);
-    st.host_chain_ms += now_ms() - t0;
-    // 4. start phases up, run checkpoints, synthesis (+ overlapped download)
-    CU(cudaEventRecord(ctx->ev[3], s));
-    CU(cudaMemcpyAsync(ctx->d_carr0, ctx->h_carr0, nbc * sizeof(double), cudaMemcpyHostToDevice, s));
-    CU(launch_checkpoints(a, s));
-    CU(cudaEventRecord(ctx->ev[4], s));
-    st.launches = 2;
-    st.h2d_bytes = (int64_t) (nbc * (sizeof(BlockChanDev) + 2 * sizeof(double)));
-    st.d2h_bytes = (int64_t) (nbc * sizeof(CarrierProbe));
-    if (!dst_host) {
-        CU(launch_synth(a, s));
-        st.launches += 1;
-    } else {
-        int ichunk = 0;
-        for (int b0 = 0; b0 < nblk; b0 += kSynthChunk, ichunk++) {
-            const int nb = std::min(kSynthChunk, nblk - b0);
-            SynthArgs ac{};
-            char *dout = (char *) dst_dev + (size_t) b0 * blk_bytes;
-            fill_args(ctx, ac, b0, nb, nchan, sample_size, dout);
-            CU(launch_synth(ac, s));
+    int seg_blocks = dst_host ? kSegFirst : nblk;
+    cudaStream_t sp = dst_host ? ctx->s_pre : s;        // stream of the pre-phase
+    int rc = upload_nav(ctx, sp);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[0], s));
+    int ichunk = 0;
+    for (int b0 = 0, b1 = 0; b0 < nblk; b0 = b1, seg_blocks = kSegBlocks) {
+        b1 = std::min(nblk, b0 + seg_blocks);
+        const int nb = b1 - b0;
+        const size_t off = (size_t) b0 * nchan, cnt = (size_t) nb * nchan;
+        // 1. host pre-pass: device records + guessed start phases
+        double t0 = now_ms();
+        rc = prepare_blocks(ctx, chans, b0, b1, nchan, chain);
+        if (rc) {
+            cudaStreamSynchronize(s);
+            cudaStreamSynchronize(sp);
+            cudaStreamSynchronize(ctx->s_copy);
+            return rc;
+        }
+        st.host_chain_ms += now_ms() - t0;
+        // 2. parameters up, speculative carrier probe, probes down
+        CU(cudaMemcpyAsync(ctx->d_bc + off, ctx->h_bc + off, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, sp));
+        CU(cudaMemcpyAsync(ctx->d_guess + off, ctx->h_guess + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        SynthArgs a{};
+        fill_args(ctx, a, b0, nb, nchan, sample_size, (char *) dst_dev + (size_t) b0 * blk_bytes);
+        if (b0 == 0) CU(cudaEventRecord(ctx->ev[1], sp));
+        CU(launch_probe(a, sp));
+        if (b0 == 0) CU(cudaEventRecord(ctx->ev[2], sp));
+        CU(cudaStreamSynchronize(sp));                   // probes are in (mapped) host memory now
+        // 3. exact block-start phases (host, serial over blocks per channel, cheap)
+        t0 = now_ms();
+        st.chain_fallbacks += (int32_t) resolve_chain(ctx, chans, b0, b1, nchan, chain);
+        st.host_chain_ms += now_ms() - t0;
+        // 4. start phases up, run checkpoints, synthesis (+ overlapped download)
+        if (b0 == 0) CU(cudaEventRecord(ctx->ev[3], sp));
+        CU(cudaMemcpyAsync(ctx->d_carr0 + off, ctx->h_carr0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        CU(launch_checkpoints(a, sp));
+        if (b0 == 0) CU(cudaEventRecord(ctx->ev[4], sp));
+        if (sp != s) {                                   // synthesis of this segment waits for its checkpoints
+            CU(cudaEventRecord(ctx->ev_done[ichunk], sp));
+            CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
+            ichunk++;
+        }
+        st.launches += 2;
+        st.h2d_bytes += (int64_t) (cnt * (sizeof(BlockChanDev) + 2 * sizeof(double)));
+        st.d2h_bytes += (int64_t) (cnt * sizeof(CarrierProbe));
+        if (!dst_host) {
+            CU(launch_synth(a, s));
             st.launches += 1;
-            CU(cudaEventRecord(ctx->ev_done[ichunk], s));
-            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[ichunk], 0));
-            CU(cudaMemcpyAsync((char *) dst_host + (size_t) b0 * blk_bytes, dout, (size_t) nb * blk_bytes,
-                               cudaMemcpyDeviceToHost, ctx->s_copy));
-            st.d2h_bytes += (int64_t) nb * (int64_t) blk_bytes;
+        } else {
+            for (int c0 = b0; c0 < b1; c0 += kSynthChunk, ichunk++) {
+                const int nc = std::min(kSynthChunk, b1 - c0);
+                SynthArgs ac{};
+                char *dout = (char *) dst_dev + (size_t) c0 * blk_bytes;
+                fill_args(ctx, ac, c0, nc, nchan, sample_size, dout);
+                CU(launch_synth(ac, s));
+                st.launches += 1;
+                CU(cudaEventRecord(ctx->ev_done[ichunk], s));
+                CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[ichunk], 0));
+                CU(cudaMemcpyAsync((char *) dst_host + (size_t) c0 * blk_bytes, dout, (size_t) nc * blk_bytes,
+                                   cudaMemcpyDeviceToHost, ctx->s_copy));
+                st.d2h_bytes += (int64_t) nc * (int64_t) blk_bytes;
+            }
         }
     }
     CU(cudaEventRecord(ctx->ev[5], s));
-    ctx->last = a;
+    SynthArgs all{};
+    fill_args(ctx, all, 0, nblk, nchan, sample_size, dst_dev);
+    ctx->last = all;
     ctx->have_last = true;
     if (carr_phase_out)
         for (int c = 0; c < nchan; c++) carr_phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
@@ -305,15 +386,18 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     if (stats) {
         CU(cudaEventSynchronize(ctx->ev[5]));
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        st.h2d_ms = ms;
+        // per-kernel times of the FIRST segment (the only one when dst_host == NULL) ...
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
         st.probe_kernel_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
         st.checkpoint_kernel_ms = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
-        st.synth_kernel_ms = ms;
-        st.kernel_ms = st.probe_kernel_ms + st.checkpoint_kernel_ms + st.synth_kernel_ms;
+        if (!dst_host) {
+            cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+            st.synth_kernel_ms = ms;
+        }
+        // ... and the whole span of the call's stream
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
+        st.kernel_ms = ms;
         *stats = st;
     }
     return GPSB200_OK;
@@ -387,7 +471,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     ctx->cfg = *cfg;
     gpsb200_config_t &c = ctx->cfg;
     if (c.run_samples == 0) c.run_samples = 2400;
-    if (c.host_threads <= 0) c.host_threads = (int) std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (c.host_threads <= 0) c.host_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (c.max_nav_frames <= 0) c.max_nav_frames = 1;
     if (c.max_chan < 1 || c.max_chan > GPSB200_MAX_CHAN || c.max_blocks < 1 || c.run_samples < 32 ||
         c.run_samples % 32 != 0 || GPSB200_BLOCK_SAMPLES % c.run_samples != 0) {
@@ -395,6 +479,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
         return GPSB200_ERR_ARG;
     }
     ctx->nruns = GPSB200_BLOCK_SAMPLES / c.run_samples;
+    ctx->pool.reset(new WorkerPool(std::min(c.host_threads, c.max_chan)));
     *out = ctx;   // from here on errors are reported through the context
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -402,8 +487,9 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaSetDevice(c.device));
     CU(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_pre, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
-    const int nchunk = (c.max_blocks + kSynthChunk - 1) / kSynthChunk;
+    const int nchunk = (c.max_blocks + kSynthChunk - 1) / kSynthChunk + (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 2;
     ctx->ev_done.resize(nchunk);
     for (auto &e : ctx->ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const size_t nbc = (size_t) c.max_blocks * c.max_chan;
@@ -415,8 +501,10 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_guess, nbc * sizeof(double), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_carr0, nbc * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_carr0, nbc * sizeof(double), cudaHostAllocDefault));
-    CU(cudaMalloc(&ctx->d_probe, nbc * sizeof(CarrierProbe)));
-    CU(cudaHostAlloc(&ctx->h_probe, nbc * sizeof(CarrierProbe), cudaHostAllocDefault));
+    // probe results are written by the kernel straight into mapped pinned host memory: a
+    // copy-engine download would queue behind the large result downloads of earlier segments
+    CU(cudaHostAlloc(&ctx->h_probe, nbc * sizeof(CarrierProbe), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **) &ctx->d_probe, ctx->h_probe, 0));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
     CU(cudaMalloc(&ctx->d_nav, navb));
     CU(cudaHostAlloc(&ctx->h_nav, navb, cudaHostAllocDefault));
@@ -439,6 +527,7 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     if (!ctx) return;
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
+    if (ctx->s_pre) cudaStreamSynchronize(ctx->s_pre);
     cudaFree(ctx->d_bc);
     cudaFreeHost(ctx->h_bc);
     cudaFree(ctx->d_ck);
@@ -447,7 +536,6 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFreeHost(ctx->h_guess);
     cudaFree(ctx->d_carr0);
     cudaFreeHost(ctx->h_carr0);
-    cudaFree(ctx->d_probe);
     cudaFreeHost(ctx->h_probe);
     cudaFree(ctx->d_nav);
     cudaFreeHost(ctx->h_nav);
@@ -459,6 +547,7 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_pre) cudaStreamDestroy(ctx->s_pre);
     delete ctx;
 }
 

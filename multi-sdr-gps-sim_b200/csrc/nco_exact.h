@@ -324,7 +324,10 @@ GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, 
     return n0 - n;
 }
 
-GPSB_HD void carrier_probe(double guess, double c, int64_t n, CarrierProbe &o) {
+// One parity variant v of the probe (the device runs the two variants in different threads;
+// each repeats the short walk to the first wrap). Fills n_w/x_w (identical for both v) and
+// the v-th end state and margins.
+GPSB_HD void carrier_probe_variant(double guess, double c, int64_t n, int v, CarrierProbe &o) {
     double x = guess;
     bool wrapped = false, ok = true;
     const int64_t nw = carrier_walk(x, c, n, true, wrapped, ok, nullptr, nullptr);
@@ -332,24 +335,26 @@ GPSB_HD void carrier_probe(double guess, double c, int64_t n, CarrierProbe &o) {
     if (!wrapped || !ok) {
         o.n_w = -1;
         o.x_w = x;
-        o.x_end[0] = o.x_end[1] = x;
-        o.m_pos[0] = o.m_pos[1] = o.m_neg[0] = o.m_neg[1] = 0.0;
+        o.x_end[v] = x;
+        o.m_pos[v] = o.m_neg[v] = 0.0;
         return;
     }
     o.n_w = (int32_t) nw;
     o.x_w = x;
-    const double G = carrier_grid(c);
-    for (int v = 0; v < 2; v++) {
-        double xv = o.x_w + (v ? G : 0.0);     // exact: x_w is a multiple of G
-        double mp = 1.0, mn = 1.0;
-        bool w2, ok2;
-        // a parity partner that left [0,1) (x_w at the very edge) is simply unusable
-        if (!(xv >= 0.0 && xv < 1.0)) mp = mn = 0.0;
-        else carrier_walk(xv, c, n - nw, false, w2, ok2, &mp, &mn);
-        o.x_end[v] = xv;
-        o.m_pos[v] = mp;
-        o.m_neg[v] = mn;
-    }
+    double xv = x + (v ? carrier_grid(c) : 0.0);       // exact: x_w is a multiple of G
+    double mp = 1.0, mn = 1.0;
+    bool w2, ok2;
+    // a parity partner that left [0,1) (x_w at the very edge) is simply unusable
+    if (!(xv >= 0.0 && xv < 1.0)) mp = mn = 0.0;
+    else carrier_walk(xv, c, n - nw, false, w2, ok2, &mp, &mn);
+    o.x_end[v] = xv;
+    o.m_pos[v] = mp;
+    o.m_neg[v] = mn;
+}
+
+GPSB_HD void carrier_probe(double guess, double c, int64_t n, CarrierProbe &o) {
+    carrier_probe_variant(guess, c, n, 0, o);
+    carrier_probe_variant(guess, c, n, 1, o);
 }
 
 // Exact end-of-block carrier phase from the true start s and the probe of a guessed start.

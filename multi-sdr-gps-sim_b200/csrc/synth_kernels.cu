@@ -51,20 +51,33 @@ __device__ __forceinline__ bool map_block_chan(const SynthArgs &a, int idx, int 
 }
 
 __global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
+    // two threads per (block, channel): one per parity variant (nco_exact.h)
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const int per_v = nblk_pad * a.nchan;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = idx / per_v;
+    idx -= v * per_v;
     int b, c;
-    if (!map_block_chan(a, blockIdx.x * blockDim.x + threadIdx.x, b, c)) return;
+    if (v > 1 || !map_block_chan(a, idx, b, c)) return;
     const size_t i = (size_t) b * a.nchan + c;
     const BlockChanDev p = a.bc[i];
     CarrierProbe o;
     if (p.prn > 0) {
-        carrier_probe(a.guess[i], p.c_carr, kBlockSamples, o);
+        carrier_probe_variant(a.guess[i], p.c_carr, kBlockSamples, v, o);
     } else {
         o.n_w = -1;
-        o.pad = 0;
         o.x_w = 0.0;
-        o.x_end[0] = o.x_end[1] = o.m_pos[0] = o.m_pos[1] = o.m_neg[0] = o.m_neg[1] = 0.0;
+        o.x_end[v] = o.m_pos[v] = o.m_neg[v] = 0.0;
     }
-    a.probe[i] = o;
+    CarrierProbe *dst = a.probe + i;
+    if (v == 0) {
+        dst->x_w = o.x_w;
+        dst->n_w = o.n_w;
+        dst->pad = 0;
+    }
+    dst->x_end[v] = o.x_end[v];
+    dst->m_pos[v] = o.m_pos[v];
+    dst->m_neg[v] = o.m_neg[v];
 }
 
 __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
@@ -366,7 +379,7 @@ cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {
 
 cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s) {
     const int nblk_pad = (a.nblk + 31) & ~31;
-    const long total = (long) nblk_pad * a.nchan;
+    const long total = 2L * nblk_pad * a.nchan;
     const int threads = 128;
     k_probe<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
     return cudaGetLastError();
