@@ -91,6 +91,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+def host_cpus():
+    """CPUs this process may really use: the cgroup quota when there is one, else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def ref_binary(nchan, fast=False):
     name = "ref_run%d%s" % (32 if nchan > 12 else 12, "_fast" if fast else "")
     p = os.path.join(ROOT, "oracle", "_ref", name)
@@ -133,7 +145,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     nchan = args.chan
-    procs = max(1, os.cpu_count() or 1)
+    procs = host_cpus()
     secs = 5.0 if nchan > 12 else 10.0       # 49 / 99 blocks per process and step: a few seconds of CPU
     vals = []
     for i in range(args.warmup + args.steps):
@@ -219,7 +231,7 @@ def main():
     bytes_per_sample = 4 if args.iq16 else 2
     # this rank's slice of one continuous scenario, seeded with the exact carrier phase at its first block
     chans, nav = gps.synthetic_chans(nblk, nchan, seed=2024, block0=rank * nblk)
-    host_threads = max(1, min(16, (os.cpu_count() or 8) // max(1, world)))
+    host_threads = max(1, min(16, host_cpus() // max(1, world)))
     t_seed0 = time.time()
     if rank > 0:
         prefix, _ = gps.synthetic_chans(rank * nblk, nchan, seed=2024, block0=0)
@@ -309,7 +321,10 @@ def main():
             "kernels": {"k_probe_ms": round(pr_ms, 3), "k_checkpoints_ms": round(ck_ms, 3),
                         "k_synth_ms": round(syn_ms, 3)},
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         # ncu --set full (profiles/r1_ncu_metrics.csv): dram read+write of one 600-block int8
+                         # launch = 59.2 + 306.3 MB for 360 MB of algorithmic bytes; scaled to this launch
+                         "traffic": (int(alg_bytes * (59.2 + 306.3) / 360.0) if not args.iq16 else None),
                          "peak_source": peak_src,
                          "note": "path is issue-slot / shared-memory bound (~16 SASS instructions per channel-sample "
                                  "warp-step), not HBM bound; see DESIGN.md and profiles/"},

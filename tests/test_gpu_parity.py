@@ -145,3 +145,33 @@ def test_errors_are_loud():
         assert e.value.code == -1
         with pytest.raises(gps.GpsB200Error):
             ctx.synth_blocks(np.concatenate([ch, ch]), 1)      # nblk > max_blocks
+
+
+def test_full_size_300s_32ch_int8_properties():
+    """BASELINE configs[2] at full size (2999 blocks x 32 channels = 899.7 Msamples, 1.8 GB):
+    the segmented host-destination path equals the single-segment device path byte for byte,
+    and sampled blocks equal the CPU oracle started from carrier phases obtained by the
+    SEQUENTIAL exact chain (gpsb200_carrier_chain) -- i.e. independently of the speculative
+    parallel-in-time chain the pipeline uses."""
+    import torch
+    import zlib
+    nblk, nchan = 2999, 32
+    ch, nav = gps.synthetic_chans(nblk, nchan, seed=2024)
+    with gps.Context(nchan, nblk) as ctx:
+        ctx.set_nav_frames(nav)
+        host = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int8, pin_memory=True)
+        out, cp, st = ctx.synth_blocks(ch, 1, out=host.numpy(), want_stats=True)
+        dev = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int8, device="cuda")
+        cpd = ctx.synth_blocks_device(ch, 1, dev.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(host.cuda(), dev)
+        assert np.array_equal(cp, cpd)
+    assert st.chain_fallbacks < 0.01 * nblk * nchan
+    assert np.array_equal(cp, gps.carrier_chain(ch, threads=8))          # speculative == sequential chain
+    for b in (1, 1234, 2998):
+        start = gps.carrier_chain(ch[:b], threads=8)
+        one = ch[b:b + 1].copy()
+        one["carr_phase"][0] = start
+        want, _ = scenario.oracle_run(one, nav, 1)
+        got = out[b * gps.BLOCK_ELEMS:(b + 1) * gps.BLOCK_ELEMS]
+        assert zlib.crc32(got.tobytes()) == zlib.crc32(want.tobytes()), b
