@@ -142,6 +142,36 @@ int gpsb200_carrier_probe_fixup(double start, double guess, double f_carr, int64
 /* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
 
+/* ---- scenario engine: the reference's host path outside the sample loop -------------
+ * RINEX-2 navigation file + location/motion -> the gpsb200_chan_t records and NAV frames the
+ * synthesis consumes; bit-identical to what the reference's producer computes (RINEX reader
+ * gps.c:1131-1505, satpos/computeRange/ionosphericDelay gps.c:508-611,1893-2026,
+ * computeCodePhase gps.c:2033-2064, eph2sbf/generateNavMsg/computeChecksum gps.c:617-884,
+ * 1008-1072,2066-2140, allocateChannel gps.c:2142-2235, the 10 Hz / 30 s loop gps.c:2703-2765,
+ * 2870-2932). Almanac pages are not generated (reference run with its almanac disabled). */
+typedef struct gpsb200_scenario_config {
+    const char *nav_file;          /* -e: RINEX v2 navigation file */
+    const char *motion_file;       /* -m: ECEF motion csv "t,x,y,z" at 10 Hz, NULL = static */
+    double lat_deg, lon_deg, height_m;   /* -l */
+    int32_t duration_ds;           /* -d in 0.1 s units: (int)(seconds*10+0.5) (gps-sim.c:140); blocks = this - 1 */
+    int32_t max_chan;              /* 12 as shipped (gps.h:36); up to 32 */
+    int32_t ionosphere_enable;     /* 1 = reference default (-I clears it) */
+    int32_t pluto_gain;            /* 1 = gain x 2 (gps.c:2759-2763) */
+    int32_t start_year, start_month, start_day, start_hour, start_min;   /* -s; year 0: first ephemeris epoch */
+    int32_t reserved;
+    double start_sec;
+} gpsb200_scenario_config_t;
+typedef struct gpsb200_scenario gpsb200_scenario_t;
+
+int gpsb200_scenario_create(const gpsb200_scenario_config_t *cfg, gpsb200_scenario_t **out);
+void gpsb200_scenario_destroy(gpsb200_scenario_t *s);
+const char *gpsb200_scenario_error(const gpsb200_scenario_t *s);
+int gpsb200_scenario_blocks(const gpsb200_scenario_t *s);        /* number of 0.1 s blocks */
+int gpsb200_scenario_channels(const gpsb200_scenario_t *s);
+int gpsb200_scenario_nav_frames(const gpsb200_scenario_t *s);
+const gpsb200_chan_t *gpsb200_scenario_chans(const gpsb200_scenario_t *s);   /* [blocks][channels] */
+const uint32_t *gpsb200_scenario_nav(const gpsb200_scenario_t *s);           /* [frames][channels][60] */
+
 /* ---- FIFO / sink boundary: the reference's own API (fifo.h:19-62) -------------- */
 struct iq_buf {
     signed char *data8;        /* 8 bit IQ data  */

@@ -42,6 +42,16 @@ class Config(C.Structure):
                 ("max_nav_frames", C.c_int32), ("host_threads", C.c_int32), ("run_samples", C.c_int32)]
 
 
+class ScenarioConfig(C.Structure):
+    _fields_ = [("nav_file", C.c_char_p), ("motion_file", C.c_char_p),
+                ("lat_deg", C.c_double), ("lon_deg", C.c_double), ("height_m", C.c_double),
+                ("duration_ds", C.c_int32), ("max_chan", C.c_int32), ("ionosphere_enable", C.c_int32),
+                ("pluto_gain", C.c_int32),
+                ("start_year", C.c_int32), ("start_month", C.c_int32), ("start_day", C.c_int32),
+                ("start_hour", C.c_int32), ("start_min", C.c_int32), ("reserved", C.c_int32),
+                ("start_sec", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("host_chain_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("checkpoint_kernel_ms", C.c_double), ("synth_kernel_ms", C.c_double),
@@ -56,6 +66,9 @@ EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_v
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_probe_fixup",
            "gpsb200_codegen",
+           "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
+           "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
+           "gpsb200_scenario_chans", "gpsb200_scenario_nav",
            "fifo_create", "fifo_destroy", "fifo_wait_next", "fifo_wait_full", "fifo_halt", "fifo_acquire",
            "fifo_enqueue", "fifo_dequeue", "fifo_release", "fifo_set_compat_drop",
            "gpsb200_iqfile_start", "gpsb200_iqfile_stop"]
@@ -81,6 +94,16 @@ def lib():
         L.gpsb200_carrier_advance.argtypes = [C.c_double, C.c_double, C.c_int64]
         L.gpsb200_carrier_advance.restype = C.c_double
         L.gpsb200_codegen.argtypes = [C.c_int, C.c_void_p]
+        L.gpsb200_scenario_create.argtypes = [C.POINTER(ScenarioConfig), C.POINTER(C.c_void_p)]
+        L.gpsb200_scenario_destroy.argtypes = [C.c_void_p]
+        L.gpsb200_scenario_error.argtypes = [C.c_void_p]
+        L.gpsb200_scenario_error.restype = C.c_char_p
+        for fn in ("blocks", "channels", "nav_frames"):
+            getattr(L, "gpsb200_scenario_" + fn).argtypes = [C.c_void_p]
+        L.gpsb200_scenario_chans.argtypes = [C.c_void_p]
+        L.gpsb200_scenario_chans.restype = C.c_void_p
+        L.gpsb200_scenario_nav.argtypes = [C.c_void_p]
+        L.gpsb200_scenario_nav.restype = C.c_void_p
         L.gpsb200_carrier_probe_fixup.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_double)]
         L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
@@ -110,6 +133,37 @@ def carrier_chain(chans, phase_in=None, threads=16):
     if rc:
         raise GpsB200Error(rc, "gpsb200_carrier_chain")
     return out
+
+
+def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None, start=None,
+             ionosphere=True, pluto_gain=False):
+    """Run the host scenario engine. -> (chans[nblk, max_chan] CHAN_DTYPE, nav[nframes, max_chan, 60] uint32).
+    start: (y, m, d, hh, mm, sec) or None for the first ephemeris epoch."""
+    cfg = ScenarioConfig()
+    cfg.nav_file = os.fsencode(nav_file)
+    cfg.motion_file = os.fsencode(motion_file) if motion_file else None
+    cfg.lat_deg, cfg.lon_deg, cfg.height_m = lat, lon, height
+    cfg.duration_ds = int(seconds * 10.0 + 0.5)
+    cfg.max_chan = max_chan
+    cfg.ionosphere_enable = 1 if ionosphere else 0
+    cfg.pluto_gain = 1 if pluto_gain else 0
+    if start:
+        (cfg.start_year, cfg.start_month, cfg.start_day, cfg.start_hour, cfg.start_min) = [int(v) for v in start[:5]]
+        cfg.start_sec = float(start[5])
+    h = C.c_void_p()
+    L = lib()
+    rc = L.gpsb200_scenario_create(C.byref(cfg), C.byref(h))
+    try:
+        if rc:
+            raise GpsB200Error(rc, L.gpsb200_scenario_error(h).decode() if h else "gpsb200_scenario_create")
+        nblk, nch, nfr = (L.gpsb200_scenario_blocks(h), L.gpsb200_scenario_channels(h),
+                          L.gpsb200_scenario_nav_frames(h))
+        chans = np.frombuffer(C.string_at(L.gpsb200_scenario_chans(h), nblk * nch * 64), dtype=CHAN_DTYPE)
+        nav = np.frombuffer(C.string_at(L.gpsb200_scenario_nav(h), nfr * nch * 60 * 4), dtype=np.uint32)
+        return chans.reshape(nblk, nch).copy(), nav.reshape(nfr, nch, 60).copy()
+    finally:
+        if h:
+            L.gpsb200_scenario_destroy(h)
 
 
 class Context:

@@ -175,3 +175,44 @@ def test_full_size_300s_32ch_int8_properties():
         want, _ = scenario.oracle_run(one, nav, 1)
         got = out[b * gps.BLOCK_ELEMS:(b + 1) * gps.BLOCK_ELEMS]
         assert zlib.crc32(got.tobytes()) == zlib.crc32(want.tobytes()), b
+
+
+def _nav_file(tmp_path, nsat):
+    import subprocess
+    import sys
+    import os
+    nav = tmp_path / ("sky%d.nav" % nsat)
+    subprocess.check_call([sys.executable, os.path.join(scenario.ROOT, "oracle", "gen_rinex.py"),
+                           "--nsat", str(nsat), "--out", str(nav)])
+    return str(nav)
+
+
+@pytest.mark.parametrize("name,nsat,chan,secs", [("sky12_static_10s_i8", 12, 12, 10), ("sky32_static_10s_i8", 32, 32, 10),
+                                                 ("sky12_static_35s_i8", 12, 12, 35)])
+def test_config1_from_rinex_file_to_reference_stream(name, nsat, chan, secs, tmp_path):
+    """BASELINE configs[1] literally: RINEX + location + start time in, IQ stream out, no
+    reference-produced parameter anywhere -- compared with the reference's stream."""
+    g = scenario.load_golden(name)
+    ch, nav = gps.scenario(_nav_file(tmp_path, nsat), 35.681298, 139.766247, 10.0, seconds=secs, max_chan=chan,
+                           start=(2024, 1, 7, 2, 0, 0.0))
+    with gps.Context(chan, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 1)
+    assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
+
+
+def test_cli_writes_reference_iqfile_and_stock_compat_file(tmp_path):
+    import os
+    import subprocess
+    import zlib
+    exe = os.path.join(scenario.ROOT, "multi-sdr-gps-sim_b200", "gpsb200-sim")
+    nav = _nav_file(tmp_path, 12)
+    g = scenario.load_golden("sky12_static_10s_i8")
+    for extra, keep in (([], list(range(99))), (["--compat-drop"], [0] + list(range(7, 99)))):
+        out = tmp_path / ("iq%d.bin" % len(extra))
+        subprocess.check_call([exe, "-e", nav, "-l", "35.681298,139.766247,10.0", "-d", "10",
+                               "-s", "2024/01/07,02:00:00", "-o", str(out)] + extra)
+        s = np.fromfile(out, dtype=np.int8)
+        assert s.size == len(keep) * gps.BLOCK_ELEMS, (extra, s.size)
+        for row, b in zip(s.reshape(len(keep), gps.BLOCK_ELEMS), keep):
+            assert zlib.crc32(row.tobytes()) == g["crcs"][b, 0], (extra, b)
