@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS_300S)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of the finished slices")
+    ap.add_argument("--run-samples", type=int, default=0, help="device work unit (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -238,7 +239,8 @@ def main():
         chans["carr_phase"][0] = gps.sharding.start_phases(prefix, threads=host_threads)
     t_seed = time.time() - t_seed0
 
-    ctx = gps.Context(nchan, nblk, device=local, max_nav_frames=1, host_threads=host_threads)
+    ctx = gps.Context(nchan, nblk, device=local, max_nav_frames=1, host_threads=host_threads,
+                      run_samples=args.run_samples)
     ctx.set_nav_frames(nav)
     out_dev = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, device="cuda")
     # a dedicated (non-default) stream: handle 0 would mean "the context's own stream" to the C ABI,

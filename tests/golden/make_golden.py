@@ -29,12 +29,17 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 LOC = "35.681298,139.766247,10.0"
 START = "2024/01/07,02:00:00"   # = toc of the synthetic ephemerides (avoids date2gps on a zero date)
 
+from motion_track import write_motion  # noqa: E402
+
+
 SCENARIOS = {
     # name: (nsat, binary, seconds, extra args, keep verbatim blocks)
     "sky12_static_10s_i8": (12, "ref_dump12", 10, [], [0, 98]),
     "sky12_static_35s_i8": (12, "ref_dump12", 35, [], []),
     "sky12_circle_10s_i16": (12, "ref_dump12", 10, ["--iq16", "-m", "/root/reference/circle.csv"], [0]),
     "sky32_static_10s_i8": (32, "ref_dump32", 10, [], [0]),
+    # BASELINE configs[3]: motion file + --iq16 + 60 s; digests only (parameters come from the scenario engine)
+    "sky12_track_60s_i16": (12, "ref_dump12", 60, ["--iq16", "-m", "@MOTION"], []),
 }
 
 
@@ -45,6 +50,10 @@ def run(name):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "gen_rinex.py"),
                                "--nsat", str(nsat), "--out", nav])
         iq, par = os.path.join(td, "iq.bin"), os.path.join(td, "p.bin")
+        if "@MOTION" in extra:
+            mot = os.path.join(td, "track.csv")
+            write_motion(mot, int(secs * 10))
+            extra = [mot if x == "@MOTION" else x for x in extra]
         subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOC, "-d", str(secs),
                                "-s", START, "--iq", iq, "--params", par] + extra,
                               stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
@@ -56,9 +65,14 @@ def run(name):
         assert stream.size == nblk * 600000, (stream.size, nblk)
         crcs = refdump.block_crcs(stream)
         blocks = stream.reshape(nblk, 600000)
+        if name.endswith("60s_i16"):
+            ch_keep = ch[:2]            # parameters are recomputed by the scenario engine in the test
+            nav_all = refdump.nav_table(p)[:2]
+        else:
+            ch_keep, nav_all = ch, refdump.nav_table(p)
         out = dict(
             max_chan=np.int32(p["max_chan"]), sample_size=np.int32(p["sample_size"]),
-            chans=ch, nav_words=refdump.nav_table(p), crcs=crcs,
+            chans=ch_keep, nav_words=nav_all, crcs=crcs,
             keep_idx=np.array(keep, np.int32),
             keep_blocks=np.stack([blocks[i] for i in keep]) if keep else np.zeros((0, 600000), dt),
             sin512=p["sin512"], cos512=p["cos512"],
@@ -68,7 +82,7 @@ def run(name):
         # NAV words change every 300 blocks: store one copy per distinct frame.
         nw = out.pop("nav_words")
         frames, idx = [], np.zeros(nblk, np.int32)
-        for b in range(nblk):
+        for b in range(nw.shape[0]):
             if not frames or not np.array_equal(frames[-1], nw[b]):
                 frames.append(nw[b])
             idx[b] = len(frames) - 1

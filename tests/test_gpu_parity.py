@@ -216,3 +216,19 @@ def test_cli_writes_reference_iqfile_and_stock_compat_file(tmp_path):
         assert s.size == len(keep) * gps.BLOCK_ELEMS, (extra, s.size)
         for row, b in zip(s.reshape(len(keep), gps.BLOCK_ELEMS), keep):
             assert zlib.crc32(row.tobytes()) == g["crcs"][b, 0], (extra, b)
+
+
+def test_config3_motion_track_60s_int16_from_rinex(tmp_path):
+    """BASELINE configs[3] (motion file, --iq16, 60 s = 599 blocks, 718.8 MB): scenario engine +
+    CUDA synthesis against the reference's stream for the same generated track."""
+    import motion_track
+    g = scenario.load_golden("sky12_track_60s_i16")
+    mot = tmp_path / "track.csv"
+    motion_track.write_motion(str(mot), 600)
+    ch, nav = gps.scenario(_nav_file(tmp_path, 12), 35.681298, 139.766247, 10.0, seconds=60, max_chan=12,
+                           motion_file=str(mot), start=(2024, 1, 7, 2, 0, 0.0))
+    assert ch.shape == (599, 12)
+    with gps.Context(12, 599, max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 2)
+    assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
