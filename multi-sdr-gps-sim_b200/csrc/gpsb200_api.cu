@@ -113,6 +113,7 @@ private:
 struct gpsb200_ctx {
     gpsb200_config_t cfg{};
     int nruns = 0;
+    int units = 1, unit_samples = GPSB200_BLOCK_SAMPLES;   // carrier-chain units per block
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> ev_done;      // one per synthesis chunk
@@ -171,7 +172,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 const size_t i = (size_t) b * nchan + c;
                 BlockChanDev &o = ctx->h_bc[i];
                 memset(&o, 0, sizeof o);
-                ctx->h_guess[i] = 0.0;
+                for (int u = 0; u < ctx->units; u++) ctx->h_guess[((size_t) b * ctx->units + u) * nchan + c] = 0.0;
                 if (in.prn <= 0) continue;
                 if (in.prn > 32 || in.iword < 0 || in.iword >= GPSB200_NAV_WORDS || in.ibit < 0 || in.ibit >= 30 ||
                     in.icode < 0 || in.icode >= 20 || in.nav_frame < 0 || in.nav_frame >= ctx->cfg.max_nav_frames ||
@@ -194,12 +195,15 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 o.prn = in.prn;
                 o.nav0 = (uint32_t) in.iword | ((uint32_t) in.ibit << 8) | ((uint32_t) in.icode << 16);
                 o.frame = in.nav_frame;
-                double g = (double) acc;
-                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
-                ctx->h_guess[i] = g;
-                acc += (long double) GPSB200_BLOCK_SAMPLES *
-                       ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
-                acc -= floorl(acc);
+                const long double per_unit = (long double) ctx->unit_samples *
+                                             ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
+                for (int u = 0; u < ctx->units; u++) {
+                    double g = (double) acc;
+                    if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                    ctx->h_guess[((size_t) b * ctx->units + u) * nchan + c] = g;
+                    acc += per_unit;
+                    acc -= floorl(acc);
+                }
             }
         }
     });
@@ -227,22 +231,25 @@ int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int
             for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
-                ctx->h_carr0[i] = 0.0;
+                for (int u = 0; u < ctx->units; u++) ctx->h_carr0[((size_t) b * ctx->units + u) * nchan + c] = 0.0;
                 if (in.prn <= 0) {
                     st.prn = 0;
                     continue;
                 }
                 if (is_fresh(chans, b, c, nchan)) st.phase = in.carr_phase;
                 st.prn = in.prn;
-                ctx->h_carr0[i] = st.phase;
                 const double cc = ctx->h_bc[i].c_carr;
-                double xe;
-                if (carrier_fixup(st.phase, cc, ctx->h_probe[i], xe)) {
-                    st.phase = xe;
-                } else {
-                    int64_t dummy = 0;
-                    nco_advance<NCO_CARRIER>(st.phase, cc, GPSB200_BLOCK_SAMPLES, dummy);
-                    ++fallbacks[c];
+                for (int u = 0; u < ctx->units; u++) {
+                    const size_t iu = ((size_t) b * ctx->units + u) * nchan + c;
+                    ctx->h_carr0[iu] = st.phase;
+                    double xe;
+                    if (carrier_fixup(st.phase, cc, ctx->h_probe[iu], xe)) {
+                        st.phase = xe;
+                    } else {
+                        int64_t dummy = 0;
+                        nco_advance<NCO_CARRIER>(st.phase, cc, ctx->unit_samples, dummy);
+                        ++fallbacks[c];
+                    }
                 }
             }
             chain[c] = st;
@@ -256,9 +263,11 @@ int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int
 void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, int sample_size, void *out) {
     const size_t off = (size_t) blk0 * nchan;
     a.bc = ctx->d_bc + off;
-    a.carr0 = ctx->d_carr0 + off;
-    a.guess = ctx->d_guess + off;
-    a.probe = ctx->d_probe + off;
+    a.carr0 = ctx->d_carr0 + off * ctx->units;
+    a.guess = ctx->d_guess + off * ctx->units;
+    a.probe = ctx->d_probe + off * ctx->units;
+    a.units = ctx->units;
+    a.unit_samples = ctx->unit_samples;
     a.ck = ctx->d_ck + off * ctx->nruns;
     a.nav = ctx->d_nav;
     a.chipbits = ctx->d_chips;
@@ -329,7 +338,8 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         st.host_chain_ms += now_ms() - t0;
         // 2. parameters up, speculative carrier probe, probes down
         CU(cudaMemcpyAsync(ctx->d_bc + off, ctx->h_bc + off, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, sp));
-        CU(cudaMemcpyAsync(ctx->d_guess + off, ctx->h_guess + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        const size_t offu = off * ctx->units, cntu = cnt * ctx->units;
+        CU(cudaMemcpyAsync(ctx->d_guess + offu, ctx->h_guess + offu, cntu * sizeof(double), cudaMemcpyHostToDevice, sp));
         SynthArgs a{};
         fill_args(ctx, a, b0, nb, nchan, sample_size, (char *) dst_dev + (size_t) b0 * blk_bytes);
         if (b0 == 0) CU(cudaEventRecord(ctx->ev[1], sp));
@@ -342,7 +352,7 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         st.host_chain_ms += now_ms() - t0;
         // 4. start phases up, run checkpoints, synthesis (+ overlapped download)
         if (b0 == 0) CU(cudaEventRecord(ctx->ev[3], sp));
-        CU(cudaMemcpyAsync(ctx->d_carr0 + off, ctx->h_carr0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        CU(cudaMemcpyAsync(ctx->d_carr0 + offu, ctx->h_carr0 + offu, cntu * sizeof(double), cudaMemcpyHostToDevice, sp));
         CU(launch_checkpoints(a, sp));
         if (b0 == 0) CU(cudaEventRecord(ctx->ev[4], sp));
         if (sp != s) {                                   // synthesis of this segment waits for its checkpoints
@@ -351,8 +361,8 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
             ichunk++;
         }
         st.launches += 2;
-        st.h2d_bytes += (int64_t) (cnt * (sizeof(BlockChanDev) + 2 * sizeof(double)));
-        st.d2h_bytes += (int64_t) (cnt * sizeof(CarrierProbe));
+        st.h2d_bytes += (int64_t) (cnt * sizeof(BlockChanDev) + cntu * 2 * sizeof(double));
+        st.d2h_bytes += (int64_t) (cntu * sizeof(CarrierProbe));
         if (!dst_host) {
             CU(launch_synth(a, s));
             st.launches += 1;
@@ -479,6 +489,17 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
         return GPSB200_ERR_ARG;
     }
     ctx->nruns = GPSB200_BLOCK_SAMPLES / c.run_samples;
+    // Carrier-chain units per block. 1 = whole blocks (default). Finer units (GPSB200_UNITS=5) give
+    // the latency-bound walk kernels more, shorter threads, but measured on B200 the 5x larger
+    // probe table written to mapped host memory and the 5x longer host scan cost more than they save
+    // (k_probe 3.2 -> 6.7 ms, host 3.2 -> 8.9 ms at 32 channels), so this stays an experiment knob.
+    if (const char *ev = getenv("GPSB200_UNITS")) {
+        const int u = atoi(ev);
+        if (u > 1 && GPSB200_BLOCK_SAMPLES % u == 0 && (GPSB200_BLOCK_SAMPLES / u) % c.run_samples == 0) {
+            ctx->units = u;
+            ctx->unit_samples = GPSB200_BLOCK_SAMPLES / u;
+        }
+    }
     ctx->pool.reset(new WorkerPool(std::min(c.host_threads, c.max_chan)));
     *out = ctx;   // from here on errors are reported through the context
     int ndev = 0;
@@ -497,13 +518,14 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_bc, nbc * sizeof(BlockChanDev), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_ck, nbc * ctx->nruns * sizeof(RunCkpt)));
     CU(cudaMalloc(&ctx->d_carr_end, nbc * sizeof(double)));
-    CU(cudaMalloc(&ctx->d_guess, nbc * sizeof(double)));
-    CU(cudaHostAlloc(&ctx->h_guess, nbc * sizeof(double), cudaHostAllocDefault));
-    CU(cudaMalloc(&ctx->d_carr0, nbc * sizeof(double)));
-    CU(cudaHostAlloc(&ctx->h_carr0, nbc * sizeof(double), cudaHostAllocDefault));
+    const size_t nbu = nbc * ctx->units;
+    CU(cudaMalloc(&ctx->d_guess, nbu * sizeof(double)));
+    CU(cudaHostAlloc(&ctx->h_guess, nbu * sizeof(double), cudaHostAllocDefault));
+    CU(cudaMalloc(&ctx->d_carr0, nbu * sizeof(double)));
+    CU(cudaHostAlloc(&ctx->h_carr0, nbu * sizeof(double), cudaHostAllocDefault));
     // probe results are written by the kernel straight into mapped pinned host memory: a
     // copy-engine download would queue behind the large result downloads of earlier segments
-    CU(cudaHostAlloc(&ctx->h_probe, nbc * sizeof(CarrierProbe), cudaHostAllocMapped));
+    CU(cudaHostAlloc(&ctx->h_probe, nbu * sizeof(CarrierProbe), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void **) &ctx->d_probe, ctx->h_probe, 0));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
     CU(cudaMalloc(&ctx->d_nav, navb));

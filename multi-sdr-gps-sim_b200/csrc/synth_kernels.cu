@@ -51,19 +51,23 @@ __device__ __forceinline__ bool map_block_chan(const SynthArgs &a, int idx, int 
 }
 
 __global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
-    // two threads per (block, channel): one per parity variant (nco_exact.h)
-    const int nblk_pad = (a.nblk + 31) & ~31;
+    // two threads per (block, unit, channel): one per parity variant (nco_exact.h);
+    // "block" of the mapping = (block, unit) pair, so a warp is 32 consecutive units of one channel
+    SynthArgs m = a;
+    m.nblk = a.nblk * a.units;
+    const int nblk_pad = (m.nblk + 31) & ~31;
     const int per_v = nblk_pad * a.nchan;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = idx / per_v;
     idx -= v * per_v;
-    int b, c;
-    if (v > 1 || !map_block_chan(a, idx, b, c)) return;
-    const size_t i = (size_t) b * a.nchan + c;
-    const BlockChanDev p = a.bc[i];
+    int bu, c;
+    if (v > 1 || !map_block_chan(m, idx, bu, c)) return;
+    const int b = bu / a.units;
+    const size_t i = (size_t) bu * a.nchan + c;
+    const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
     CarrierProbe o;
     if (p.prn > 0) {
-        carrier_probe_variant(a.guess[i], p.c_carr, kBlockSamples, v, o);
+        carrier_probe_variant(a.guess[i], p.c_carr, a.unit_samples, v, o);
     } else {
         o.n_w = -1;
         o.x_w = 0.0;
@@ -81,18 +85,16 @@ __global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
-    // two roles per (block, channel): role 0 walks the code NCO (+ NAV position), role 1 the carrier
+    // role 0: one thread per (block, channel) walks the code NCO (+ NAV position) through the block;
+    // role 1..: one thread per (block, unit, channel) walks the carrier through its unit
     const int nblk_pad = (a.nblk + 31) & ~31;
-    const int per_role = nblk_pad * a.nchan;
+    const int per_code = nblk_pad * a.nchan;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int role = idx / per_role;
-    idx -= role * per_role;
-    int b, c;
-    if (role > 1 || !map_block_chan(a, idx, b, c)) return;
-    const size_t i = (size_t) b * a.nchan + c;
-    const BlockChanDev p = a.bc[i];
-    RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
-    if (role == 0) {
+    if (idx < per_code) {
+        int b, c;
+        if (!map_block_chan(a, idx, b, c)) return;
+        const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
+        RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
         double y = p.code0;
         int iword = p.nav0 & 0xFF, ibit = (p.nav0 >> 8) & 0xFF, icode = (p.nav0 >> 16) & 0xFF;
         for (int r = 0; r < a.nruns; r++) {
@@ -105,16 +107,25 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
             nco_advance<NCO_CODE>(y, p.c_code, a.run_samples, periods);
             nav_advance(iword, ibit, icode, periods);
         }
-    } else {
-        double x = a.carr0[i];
-        for (int r = 0; r < a.nruns; r++) {
-            ck[(size_t) r * a.nchan].x = x;
-            if (p.prn <= 0) continue;
-            int64_t dummy = 0;
-            nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
-        }
-        if (a.carr_end) a.carr_end[i] = x;
+        return;
     }
+    idx -= per_code;
+    SynthArgs m = a;
+    m.nblk = a.nblk * a.units;
+    int bu, c;
+    if (!map_block_chan(m, idx, bu, c)) return;
+    const int b = bu / a.units, u = bu - b * a.units;
+    const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
+    const int runs_per_unit = a.unit_samples / a.run_samples;
+    RunCkpt *ck = a.ck + ((size_t) b * a.nruns + (size_t) u * runs_per_unit) * a.nchan + c;
+    double x = a.carr0[(size_t) bu * a.nchan + c];
+    for (int r = 0; r < runs_per_unit; r++) {
+        ck[(size_t) r * a.nchan].x = x;
+        if (p.prn <= 0) continue;
+        int64_t dummy = 0;
+        nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
+    }
+    if (a.carr_end && u == a.units - 1) a.carr_end[(size_t) b * a.nchan + c] = x;
 }
 
 // ---------------------------------------------------------------------------------
@@ -370,15 +381,15 @@ void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *sme
 }
 
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {
-    const int nblk_pad = (a.nblk + 31) & ~31;
-    const long total = 2L * nblk_pad * a.nchan;
+    const int nblk_pad = (a.nblk + 31) & ~31, nbu_pad = (a.nblk * a.units + 31) & ~31;
+    const long total = (long) (nblk_pad + nbu_pad) * a.nchan;
     const int threads = 128;
     k_checkpoints<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s) {
-    const int nblk_pad = (a.nblk + 31) & ~31;
+    const int nblk_pad = (a.nblk * a.units + 31) & ~31;
     const long total = 2L * nblk_pad * a.nchan;
     const int threads = 128;
     k_probe<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);

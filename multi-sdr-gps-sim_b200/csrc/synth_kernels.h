@@ -36,15 +36,19 @@ struct CarrierProbe;          // nco_exact.h
 
 struct SynthArgs {
     const BlockChanDev *bc;   // [nblk][nchan]
-    const double *carr0;      // [nblk][nchan] exact carrier phase at the first sample of each block
-    const double *guess;      // [nblk][nchan] guessed start phases for the speculative probe
-    CarrierProbe *probe;      // [nblk][nchan] probe results
+    // The carrier chain is resolved in UNITS: a block is cut into `units` pieces of
+    // `unit_samples` samples (a whole number of runs) so that the latency-bound walks of
+    // k_probe / k_checkpoints get `units` times more threads that are `units` times shorter.
+    const double *carr0;      // [nblk][units][nchan] exact carrier phase at the first sample of each unit
+    const double *guess;      // [nblk][units][nchan] guessed start phases for the speculative probe
+    CarrierProbe *probe;      // [nblk][units][nchan] probe results
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
     double *carr_end;         // [nblk][nchan] carrier phase after the block (diagnostic / chain check)
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
+    int units, unit_samples;
 };
 
 // Speculative carrier walk of every (block, channel) from a guessed start phase (nco_exact.h).
