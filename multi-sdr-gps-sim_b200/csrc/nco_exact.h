@@ -194,8 +194,19 @@ GPSB_HD WalkConst walk_const(double c) {
 // One iteration: jump as far as provably stays inside the current binade, then (if steps
 // remain) one real step. `special` iterations (x below |c|, non-positive x, or an odd
 // mantissa in a tie binade) jump zero steps. Returns true when the real step wrapped.
+// floor of a non-negative double below 2^52, staying in the FP64 domain on the device
+// (the step counter `nd` of the walk is kept as a double there: no int<->fp conversions on
+// the loop-carried dependency chain)
+GPSB_HD double floor_nonneg(double v) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__dadd_rd(v, 0x1p52), -0x1p52);
+#else
+    return (double) (int64_t) v;
+#endif
+}
+
 template <int KIND>
-GPSB_HD bool walk_iteration(double &x, const WalkConst &w, int64_t &n, int64_t &periods, double *after_jump) {
+GPSB_HD bool walk_iteration(double &x, const WalkConst &w, double &nd, int64_t &periods, double *after_jump) {
     const uint64_t bx = f64_bits(x);
     const int ex = (int) ((bx >> 52) & 0x7FF);
     bool special = (bx >> 63) || !(x >= w.ac);
@@ -213,19 +224,18 @@ GPSB_HD bool walk_iteration(double &x, const WalkConst &w, int64_t &n, int64_t &
         room = x - lo;
     }
     double kq = room * w.rinv;
-    const double nd = (double) n;
     if (kq > nd) kq = nd;
     if (special) kq = 0.0;
-    const int32_t k = (int32_t) kq;                     // n <= 2^31 per call
-    const double adv = (double) k * stepd;              // exact
+    const double k = floor_nonneg(kq);                  // integer-valued, <= nd < 2^31
+    const double adv = k * stepd;                       // exact: k*R < 2^53
     x = w.neg ? x - adv : x + adv;                      // exact
-    n -= k;
+    nd -= k;
     if (after_jump) *after_jump = x;
     bool wrapped = false;
-    if (n > 0) {
+    if (nd > 0.0) {
         const double before = x;
         nco_step<KIND>(x, w.c, periods);
-        --n;
+        nd -= 1.0;
         wrapped = w.neg ? (x > before) : (x < before);
     }
     return wrapped;
@@ -239,9 +249,10 @@ GPSB_HD int nco_advance(double &x, double c, int64_t n, int64_t &periods) {
     const WalkConst w = walk_const(c);
     if (!w.fast || (KIND == NCO_CODE && w.neg)) return nco_advance_generic<KIND>(x, c, n, periods);
     int iters = 0;
-    while (n > 0) {
+    double nd = (double) n;
+    while (nd > 0.0) {
         ++iters;
-        walk_iteration<KIND>(x, w, n, periods, nullptr);
+        walk_iteration<KIND>(x, w, nd, periods, nullptr);
     }
     return iters;
 }
@@ -306,12 +317,13 @@ GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, 
         ok = false;
         return 0;
     }
-    const int64_t n0 = n;
+    const double n0 = (double) n;
+    double nd = n0;
     int64_t dummy = 0;
-    while (n > 0) {
+    while (nd > 0.0) {
         double aj;
         if (m_pos) binade_margins(x, *m_pos, *m_neg);
-        const bool wr = walk_iteration<NCO_CARRIER>(x, w, n, dummy, &aj);
+        const bool wr = walk_iteration<NCO_CARRIER>(x, w, nd, dummy, &aj);
         if (m_pos) {
             binade_margins(aj, *m_pos, *m_neg);
             binade_margins(x, *m_pos, *m_neg);
@@ -321,7 +333,7 @@ GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, 
             if (stop_at_wrap) break;
         }
     }
-    return n0 - n;
+    return (int64_t) (n0 - nd);
 }
 
 // One parity variant v of the probe (the device runs the two variants in different threads;

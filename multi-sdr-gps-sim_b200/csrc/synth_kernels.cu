@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         return (w >> (29 - ib)) & 1;                          // gps.c:2812
     };
     int dbit = nav_bit(iword, ibit);
-    const double cc9 = 9.0 * cc, dd9 = 9.0 * dd;              // conservative 8-step look-ahead (see below)
+    // conservative 8-step look-ahead (see below): 8 steps move a phase by at most 8*(|c| + ulp/2),
+    // which 9*|c| + 2^-50 (carrier, phase < 1) resp. 9*d (code, d ~ 0.34 >> ulp) always covers
+    const double cc9 = 9.0 * cc + copysign(0x1p-50, cc), dd9 = 9.0 * dd;
     int32_t *stage = &sm.stage[warp][0];
     // shared-window byte address of this lane's column of the carrier table
     const uint32_t abase = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][lane]);
