@@ -193,6 +193,13 @@ void fifo_release(struct iq_buf *buf);
  * (tail bug, fifo.c:163-168) so that iqdata.bin is byte-identical to the stock program. */
 void fifo_set_compat_drop(bool on);
 
+/* Feed a contiguous run of I/Q elements into FIFO buffers of whatever size the FIFO was created
+ * with, enqueueing each buffer when full and carrying the partly filled one to the next call --
+ * the HackRF cadence of the reference (262144-element buffers across 600000-element blocks,
+ * gps.c:2847-2856). gpsb200_fifo_push_flush enqueues a remaining partial buffer. */
+int gpsb200_fifo_push(const void *elems, size_t count, int sample_size);
+int gpsb200_fifo_push_flush(void);
+
 /* iqfile sink (sdr_iqfile.h:16-18 semantics: writes ./iqdata.bin from the FIFO). */
 int gpsb200_iqfile_start(const char *path, int sample_size);
 void gpsb200_iqfile_stop(void);

@@ -71,7 +71,7 @@ EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_v
            "gpsb200_scenario_chans", "gpsb200_scenario_nav",
            "fifo_create", "fifo_destroy", "fifo_wait_next", "fifo_wait_full", "fifo_halt", "fifo_acquire",
            "fifo_enqueue", "fifo_dequeue", "fifo_release", "fifo_set_compat_drop",
-           "gpsb200_iqfile_start", "gpsb200_iqfile_stop"]
+           "gpsb200_iqfile_start", "gpsb200_iqfile_stop", "gpsb200_fifo_push", "gpsb200_fifo_push_flush"]
 
 
 def lib():

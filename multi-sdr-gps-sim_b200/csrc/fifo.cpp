@@ -188,6 +188,46 @@ void fifo_release(struct iq_buf *buf) {
     g_free.notify_one();
 }
 
+// ---- stream -> FIFO buffers of any size (the HackRF cadence, gps.c:2847-2856) -------------
+// The HackRF sink consumes 262144-element buffers that do not align with the 600000-element
+// blocks: the reference keeps filling one acquired buffer across block boundaries and enqueues
+// it whenever it is full. Same behaviour for a contiguous stream of elements; the partly
+// filled buffer is kept for the next call (or flushed by fifo_push_flush at the end).
+static iq_buf *g_partial = nullptr;
+
+int gpsb200_fifo_push(const void *elems, size_t count, int sample_size) {
+    const char *src = (const char *) elems;
+    const size_t es = sample_size == GPSB200_SC16 ? 2 : 1;
+    while (count > 0) {
+        if (!g_partial) {
+            g_partial = fifo_acquire();
+            if (!g_partial) return GPSB200_ERR_ARG;          // halted
+        }
+        iq_buf *b = g_partial;
+        const size_t room = b->totalLength - b->validLength;
+        const size_t n = count < room ? count : room;
+        char *dst = es == 2 ? (char *) b->data16 : (char *) b->data8;
+        if (!dst) return GPSB200_ERR_ARG;                     // FIFO created for the other sample size
+        memcpy(dst + (size_t) b->validLength * es, src, n * es);
+        b->validLength += (unsigned) n;
+        src += n * es;
+        count -= n;
+        if (b->validLength == b->totalLength) {
+            fifo_enqueue(b);
+            g_partial = nullptr;
+        }
+    }
+    return GPSB200_OK;
+}
+
+int gpsb200_fifo_push_flush(void) {
+    if (g_partial) {
+        fifo_enqueue(g_partial);                              // validLength < totalLength: a short last buffer
+        g_partial = nullptr;
+    }
+    return GPSB200_OK;
+}
+
 // ---- iqfile sink (sdr_iqfile.c:22-77): dequeue -> fwrite -> release -------------------
 int gpsb200_iqfile_start(const char *path, int sample_size) {
     if (g_writer.joinable()) return GPSB200_ERR_ARG;

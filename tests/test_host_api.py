@@ -188,3 +188,45 @@ def test_fifo_compat_mode_reproduces_stock_loss_of_blocks_1_to_6():
     got = _fifo_run(True, nblocks=9)
     # stock program: block 0, then 7, 8, ... (SURVEY.md finding 3; fifo.c:163-168)
     assert got[:2] == [0, 7]
+
+
+def test_fifo_push_reproduces_hackrf_buffer_cadence():
+    # 600000-element blocks pushed into 262144-element buffers (HACKRF_TRANSFER_BUFFER_SIZE, sdr.h:34):
+    # buffers fill across block boundaries, none is enqueued partly filled (gps.c:2847-2856)
+    L = gps.lib()
+
+    class IqBuf(C.Structure):
+        pass
+    IqBuf._fields_ = [("data8", C.POINTER(C.c_int8)), ("data16", C.POINTER(C.c_int16)),
+                      ("totalLength", C.c_uint), ("validLength", C.c_uint), ("next", C.POINTER(IqBuf))]
+    L.fifo_dequeue.restype = C.POINTER(IqBuf)
+    L.fifo_release.argtypes = [C.POINTER(IqBuf)]
+    L.fifo_create.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    L.fifo_create.restype = C.c_bool
+    L.gpsb200_fifo_push.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    assert L.fifo_create(8, 262144, 1)
+    rng = np.random.default_rng(1)
+    data = rng.integers(-128, 128, size=3 * 600000, dtype=np.int8)
+    got = []
+
+    def consumer():
+        while True:
+            b = L.fifo_dequeue()
+            if not b:
+                return
+            n = b.contents.validLength
+            got.append(np.ctypeslib.as_array(b.contents.data8, shape=(n,)).copy())
+            L.fifo_release(b)
+
+    t = threading.Thread(target=consumer)
+    t.start()
+    for blk in data.reshape(3, 600000):
+        assert L.gpsb200_fifo_push(np.ascontiguousarray(blk).ctypes.data, blk.size, 1) == 0
+    L.gpsb200_fifo_push_flush()
+    L.fifo_wait_next()
+    L.fifo_halt()
+    t.join()
+    L.fifo_destroy()
+    sizes = [g.size for g in got]
+    assert sizes[:-1] == [262144] * 6 and sizes[-1] == 1800000 - 6 * 262144
+    assert np.array_equal(np.concatenate(got), data)
