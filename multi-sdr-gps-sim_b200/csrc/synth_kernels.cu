@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "nco_exact.h"
 #include "synth_kernels.h"
 #include "synth_tables.h"
@@ -133,13 +135,14 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
 // ---------------------------------------------------------------------------------
 constexpr int kAtabRows = 513;          // row 512 is never addressed (carr_phase < 1.0 always), kept as a guard
 constexpr int kMaxWarps = 24;
+constexpr int kChunkMax = 64;           // samples per chunk (chip window refill / output flush)
 
 template <int GROUP>
 struct SynthSmem {
     int32_t atab[kAtabRows][32];                 // [k][lane]: I + (Q << 16), gain-scaled (gps.c:2781-2782)
     uint32_t cabits[kChipWords][GROUP];          // [word][channel]: C/A chips, bit n = ca[n mod 1023], n < 1056
     uint32_t nav[kNavWords][GROUP];              // NAV words of this block's frame
-    int32_t stage[kMaxWarps][32 * (32 / GROUP)]; // per-warp staging of 32 samples per run
+    int32_t stage[kMaxWarps][kChunkMax * (32 / GROUP)]; // per-warp staging of one chunk of samples per run
 };
 
 template <int GROUP>
@@ -224,17 +227,56 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         return (w >> (29 - ib)) & 1;                          // gps.c:2812
     };
     int dbit = nav_bit(iword, ibit);
-    // conservative 8-step look-ahead (see below): 8 steps move a phase by at most 8*(|c| + ulp/2),
-    // which 9*|c| + 2^-50 (carrier, phase < 1) resp. 9*d (code, d ~ 0.34 >> ulp) always covers
-    const double cc9 = 9.0 * cc + copysign(0x1p-50, cc), dd9 = 9.0 * dd;
+    // Conservative 8-step look-ahead (see below): 8 steps move a phase by at most 8*(|c| + ulp/2),
+    // which 9*|c| + 2^-50 (carrier, phase < 1) resp. 9*d (code, d ~ 0.34 >> ulp) always covers.
+    // "phase + that can leave the range" is tested on the high words only (monotone for positive
+    // doubles, so the test can only err towards "at risk").
+    const double cc9 = 9.0 * fabs(cc) + 0x1p-50, dd9 = 9.0 * dd;
+    int thr_x_hi = 0x7FFFFFFF, thr_x_lo = -1;                  // cc == 0: never at risk
+    if (cc > 0.0) thr_x_hi = cc9 < 1.0 ? __double2hiint(1.0 - cc9) : 0;
+    if (cc < 0.0) thr_x_lo = __double2hiint(cc9);
+    const int thr_y = dd9 < 1023.0 ? __double2hiint(1023.0 - dd9) : 0;
     int32_t *stage = &sm.stage[warp][0];
     // shared-window byte address of this lane's column of the carrier table
     const uint32_t abase = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][lane]);
     const uint32_t *ccol = &sm.cabits[0][ch];
 
-    const int nchunks = a.run_samples / 32;
-    for (int chunk = 0; chunk < nchunks; chunk++) {
-        // Chip window of this lane for the next 32 samples (<= 12 chips): 24 chips starting at
+    // ---- quantise + pack LEN samples per run (gps.c:2833-2845) ----------------------------
+    // lane (sub, ch) converts SPL = LEN / GROUP consecutive samples of its run: contiguous bytes
+    auto flush = [&](auto len_tag, int s0) {
+        constexpr int LEN = decltype(len_tag)::value;
+        constexpr int SPL = LEN / GROUP;
+        if (!run_ok) return;
+        const size_t samp0 = (size_t) b * kBlockSamples + (size_t) r * a.run_samples + (size_t) s0 + ch * SPL;
+        uint32_t w[SPL];                                       // int16: one word per sample; int8: two samples per word
+#pragma unroll
+        for (int t = 0; t < SPL; t++) {
+            const int p = stage[sub * kChunkMax + ch * SPL + t];
+            const int iv = (int) (short) (p & 0xFFFF);         // (short) i_acc, gps.c:2834
+            const int qv = (p - iv) >> 16;                     // (short) q_acc, gps.c:2835
+            if (IQ16) {
+                w[t] = ((uint32_t) iv & 0xFFFFu) | ((uint32_t) qv << 16);
+            } else {
+                const uint32_t two = (((uint32_t) (iv >> 4)) & 0xFFu) | ((((uint32_t) (qv >> 4)) & 0xFFu) << 8);  // gps.c:2844
+                if (t & 1) w[t >> 1] |= two << 16;
+                else w[t >> 1] = two;
+            }
+        }
+        constexpr int NBYTES = SPL * (IQ16 ? 4 : 2);
+        char *dst = reinterpret_cast<char *>(a.out) + samp0 * (IQ16 ? 4 : 2);
+        if (NBYTES == 2) *reinterpret_cast<uint16_t *>(dst) = (uint16_t) w[0];
+        else if (NBYTES == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+        else if (NBYTES == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        else {
+#pragma unroll
+            for (int q = 0; q < NBYTES / 16; q++)
+                reinterpret_cast<uint4 *>(dst)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
+    };
+
+    // One chunk of len (64, or 32 for the tail of a run) consecutive samples.
+    auto do_chunk = [&](const int len, int s0) {
+        // Chip window of this lane for the chunk (<= 23 chips for 64 samples): 24 chips starting at
         // j0 = (int) code_phase, taken from the periodically extended packed code, XORed with the
         // data bit, and parked at bit 8 so that a right shift by (chip - j0) leaves the
         // "flip the sign" flag where it toggles k by 256: table[k ^ 256] = -table[k].
@@ -250,7 +292,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
             int e;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(abase + (uint32_t) kk * 128u));
             const int sum = group_sum<GROUP>(e);               // gps.c:2785-2786 over channels
-            stage[sub * 32 + i] = sum;                         // every lane of the group stores the same word
+            stage[sub * kChunkMax + i] = sum;                  // every lane of the group stores the same word
         };
         // one reference step with its wrap / NAV-bit bookkeeping (gps.c:2789-2826)
         auto step_checked = [&](double &xs, double &ys) {
@@ -277,14 +319,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
             }
         };
         // Samples go in groups of 8. A lane can tell in advance whether one of its NCOs can
-        // wrap within the next 8 steps (both phases move monotonically inside a block, so
-        // "phase + 9 steps is still in range" is a safe test). If no lane of the warp is at
-        // risk the group runs with bare additions (the common case, ~3 in 4 groups); otherwise
-        // every step carries the reference's wrap / NAV-bit bookkeeping.
+        // wrap within the next 8 steps (both phases move monotonically inside a block). If no
+        // lane of the warp is at risk the group runs with bare additions (the common case,
+        // ~3 in 4 groups at 32 channels); otherwise every step carries the reference's wrap /
+        // NAV-bit bookkeeping.
 #pragma unroll 1
-        for (int g8 = 0; g8 < 32; g8 += 8) {
-            const bool risky = ((unsigned) __double2hiint(__dadd_rn(x, cc9)) >= 0x3FF00000u) |
-                               ((unsigned) __double2hiint(__dadd_rn(y, dd9)) >= 0x408FF800u);
+        for (int g8 = 0; g8 < len; g8 += 8) {
+            const int hx = __double2hiint(x), hy = __double2hiint(y);
+            const bool risky = (hx >= thr_x_hi) | (hx <= thr_x_lo) | (hy >= thr_y);
             if (!__any_sync(0xFFFFFFFFu, risky)) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -308,39 +350,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
             }
         }
         __syncwarp();
-        // ---- quantise + pack 32 samples per run (gps.c:2833-2845) --------------------
-        if (run_ok) {
-            const size_t samp0 = (size_t) b * kBlockSamples + (size_t) r * a.run_samples + (size_t) chunk * 32 + ch * RPW;
-            if (ch * RPW < 32) {
-                if (IQ16) {
-                    uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + samp0;
-#pragma unroll
-                    for (int t = 0; t < RPW; t++) {
-                        const int p = stage[sub * 32 + ch * RPW + t];
-                        const int iv = (int) (short) (p & 0xFFFF);
-                        const int qv = (p - iv) >> 16;
-                        o[t] = ((uint32_t) iv & 0xFFFFu) | ((uint32_t) qv << 16);
-                    }
-                } else {
-                    uint32_t packed = 0;
-#pragma unroll
-                    for (int t = 0; t < RPW; t++) {
-                        const int p = stage[sub * 32 + ch * RPW + t];
-                        const int iv = (int) (short) (p & 0xFFFF);
-                        const int qv = (p - iv) >> 16;
-                        const uint32_t two = (((uint32_t) (iv >> 4)) & 0xFFu) | ((((uint32_t) (qv >> 4)) & 0xFFu) << 8);
-                        packed |= two << (16 * (t & 1));
-                        if (t & 1) {
-                            reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(a.out) + samp0)[t >> 1] = packed;
-                            packed = 0;
-                        }
-                    }
-                    if (RPW == 1) reinterpret_cast<uint16_t *>(a.out)[samp0] = (uint16_t) packed;
-                }
-            }
-        }
+        if (len == 64) flush(std::integral_constant<int, 64>(), s0);
+        else flush(std::integral_constant<int, 32>(), s0);
         __syncwarp();
-    }
+    };
+
+    int s0 = 0;
+#pragma unroll 1
+    for (; s0 < a.run_samples; s0 += 64)                       // run_samples is a multiple of 32
+        do_chunk(a.run_samples - s0 >= 64 ? 64 : 32, s0);
 }
 
 // ---------------------------------------------------------------------------------
