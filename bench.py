@@ -233,15 +233,14 @@ def main():
     # this rank's slice of one continuous scenario, seeded with the exact carrier phase at its first block
     chans, nav = gps.synthetic_chans(nblk, nchan, seed=2024, block0=rank * nblk)
     host_threads = max(1, min(16, host_cpus() // max(1, world)))
-    t_seed0 = time.time()
-    if rank > 0:
-        prefix, _ = gps.synthetic_chans(rank * nblk, nchan, seed=2024, block0=0)
-        chans["carr_phase"][0] = gps.sharding.start_phases(prefix, threads=host_threads)
-    t_seed = time.time() - t_seed0
-
     ctx = gps.Context(nchan, nblk, device=local, max_nav_frames=1, host_threads=host_threads,
                       run_samples=args.run_samples)
     ctx.set_nav_frames(nav)
+    t_seed0 = time.time()
+    if rank > 0:
+        prefix, _ = gps.synthetic_chans(rank * nblk, nchan, seed=2024, block0=0)
+        chans["carr_phase"][0] = gps.sharding.start_phases(prefix, ctx=ctx)    # exact; device probe + host fix-up
+    t_seed = max_over_ranks(time.time() - t_seed0)
     out_dev = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, device="cuda")
     # a dedicated (non-default) stream: handle 0 would mean "the context's own stream" to the C ABI,
     # and torch.cuda.Event only sees the stream it is recorded on

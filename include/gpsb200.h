@@ -132,6 +132,13 @@ double gpsb200_carrier_advance(double carr_phase, double f_carr, int64_t nsample
 int gpsb200_carrier_chain(const gpsb200_chan_t *chans, int nblk, int nchan, const double *phase_in,
                           double *phase_out, int threads);
 
+/* Same result as gpsb200_carrier_chain, but resolved with the context's parallel-in-time machinery
+ * (device probe kernel + host fix-up scan, no synthesis): ~6 ms per 3000 blocks x 32 channels
+ * instead of seconds of sequential host walking. nblk may exceed cfg.max_blocks. A rank of a
+ * time-slice sharded run seeds its first block with this. */
+int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+                                 const double *phase_in, double *phase_out);
+
 /* Host-only view of the parallel-in-time carrier chain (what the device probe kernel plus
  * the host fix-up do per block): walk `nsamples` from the GUESSED phase, then derive the exact
  * end phase of the TRUE start phase from it. Returns 1 and *end_out when the speculation is

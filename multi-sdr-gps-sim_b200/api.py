@@ -64,7 +64,7 @@ _lib = None
 
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
-           "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_probe_fixup",
+           "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
            "gpsb200_codegen",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
@@ -105,6 +105,7 @@ def lib():
         L.gpsb200_scenario_nav.argtypes = [C.c_void_p]
         L.gpsb200_scenario_nav.restype = C.c_void_p
         L.gpsb200_carrier_probe_fixup.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_double)]
+        L.gpsb200_carrier_chain_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -236,6 +237,16 @@ class Context:
                                                       C.c_void_p(dst_ptr), C.c_void_p(stream), cp.ctypes.data,
                                                       C.byref(st) if want_stats else None))
         return (cp, st) if want_stats else cp
+
+    def carrier_chain(self, chans, phase_in=None):
+        """Exact carrier phases after all blocks of chans (device probe + host fix-up, no synthesis)."""
+        a = self._chans(chans)
+        nblk, nchan = a.shape
+        out = np.zeros(nchan, np.float64)
+        pin = None if phase_in is None else np.ascontiguousarray(phase_in, dtype=np.float64)
+        self._check(lib().gpsb200_carrier_chain_device(self._h, a.ctypes.data, nblk, nchan,
+                                                       None if pin is None else pin.ctypes.data, out.ctypes.data))
+        return out
 
     def replay_device(self, dst_ptr=0, stream=0, kernel_mask=7):
         self._check(lib().gpsb200_replay_device(self._h, C.c_void_p(dst_ptr), C.c_void_p(stream), kernel_mask))

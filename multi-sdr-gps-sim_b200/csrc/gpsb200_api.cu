@@ -153,11 +153,6 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-inline bool is_fresh(const gpsb200_chan_t *chans, int b, int c, int nchan) {
-    // block 0 of a call, or a slot whose satellite changed: the caller's carr_phase applies
-    return b == 0 || chans[(size_t) (b - 1) * nchan + c].prn != chans[(size_t) b * nchan + c].prn;
-}
-
 // Host pre-pass: validate, fill the device-layout records and GUESS every block's start
 // carrier phase (closed form + expected rounding drift, long double accumulation).
 int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
@@ -167,13 +162,17 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
             long double acc = chain[c].phase;               // exact phase after block b0-1 (if any)
+            int prev_prn = chain[c].prn;                    // 0 at the start of a call: block 0 is "fresh"
             for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
                 BlockChanDev &o = ctx->h_bc[i];
                 memset(&o, 0, sizeof o);
                 for (int u = 0; u < ctx->units; u++) ctx->h_guess[((size_t) b * ctx->units + u) * nchan + c] = 0.0;
-                if (in.prn <= 0) continue;
+                if (in.prn <= 0) {
+                    prev_prn = 0;
+                    continue;
+                }
                 if (in.prn > 32 || in.iword < 0 || in.iword >= GPSB200_NAV_WORDS || in.ibit < 0 || in.ibit >= 30 ||
                     in.icode < 0 || in.icode >= 20 || in.nav_frame < 0 || in.nav_frame >= ctx->cfg.max_nav_frames ||
                     !(in.code_phase >= 0.0 && in.code_phase < 1023.0) || !(in.f_code > 0.0) ||
@@ -181,13 +180,15 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                     status[c] = GPSB200_ERR_ARG;
                     return;
                 }
-                if (is_fresh(chans, b, c, nchan)) {
+                // a slot whose satellite changed (or the first block of a call): the caller's carr_phase applies
+                if (in.prn != prev_prn) {
                     if (!(in.carr_phase >= 0.0 && in.carr_phase < 1.0)) {
                         status[c] = GPSB200_ERR_ARG;
                         return;
                     }
                     acc = in.carr_phase;
                 }
+                prev_prn = in.prn;
                 o.c_carr = in.f_carr * delt;                    // gps.c:2821
                 o.c_code = in.f_code * delt;                    // gps.c:2789
                 o.gain = in.gain;
@@ -236,7 +237,7 @@ int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int
                     st.prn = 0;
                     continue;
                 }
-                if (is_fresh(chans, b, c, nchan)) st.phase = in.carr_phase;
+                if (st.prn != in.prn) st.phase = in.carr_phase;
                 st.prn = in.prn;
                 const double cc = ctx->h_bc[i].c_carr;
                 for (int u = 0; u < ctx->units; u++) {
@@ -589,6 +590,37 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
     if (rc) return rc;
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
     return run_pipeline(ctx, chans, nblk, nchan, sample_size, dst_device, nullptr, s, carr_phase_out, stats);
+}
+
+int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+                                 const double *phase_in, double *phase_out) {
+    if (!ctx || !chans || !phase_out || nblk < 0 || nchan != ctx->cfg.max_chan) return GPSB200_ERR_ARG;
+    if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
+    cudaStream_t s = ctx->s_compute;
+    std::vector<ChainState> chain(nchan);
+    if (phase_in && nblk > 0)
+        for (int c = 0; c < nchan; c++)
+            if (chans[c].prn > 0) {
+                chain[c].prn = chans[c].prn;
+                chain[c].phase = phase_in[c];
+            }
+    for (int w0 = 0; w0 < nblk; w0 += ctx->cfg.max_blocks) {
+        const int nw = std::min(ctx->cfg.max_blocks, nblk - w0);
+        const gpsb200_chan_t *cw = chans + (size_t) w0 * nchan;
+        int rc = prepare_blocks(ctx, cw, 0, nw, nchan, chain);
+        if (rc) return rc;
+        const size_t cnt = (size_t) nw * nchan, cntu = cnt * ctx->units;
+        CU(cudaMemcpyAsync(ctx->d_bc, ctx->h_bc, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_guess, ctx->h_guess, cntu * sizeof(double), cudaMemcpyHostToDevice, s));
+        SynthArgs a{};
+        fill_args(ctx, a, 0, nw, nchan, GPSB200_SC08, nullptr);
+        CU(launch_probe(a, s));
+        CU(cudaStreamSynchronize(s));
+        resolve_chain(ctx, cw, 0, nw, nchan, chain);
+    }
+    ctx->have_last = false;
+    for (int c = 0; c < nchan; c++) phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
+    return GPSB200_OK;
 }
 
 int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream_, int kernel_mask) {

@@ -232,3 +232,50 @@ def test_config3_motion_track_60s_int16_from_rinex(tmp_path):
         ctx.set_nav_frames(nav)
         out, _ = ctx.synth_blocks(ch, 2)
     assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
+
+
+def test_device_carrier_chain_equals_sequential_host_chain():
+    ch, nav = gps.synthetic_chans(130, 32, seed=21)
+    with gps.Context(32, 50) as ctx:                      # 130 blocks > max_blocks: windows of 50
+        got = ctx.carrier_chain(ch)
+        assert np.array_equal(got, gps.carrier_chain(ch, threads=4))
+        mid = ctx.carrier_chain(ch[:70])
+        assert np.array_equal(ctx.carrier_chain(ch[70:], phase_in=mid), got)
+
+
+def test_channel_reallocation_and_gaps_vs_oracle():
+    # slots that change satellite, go idle and come back inside one call (allocateChannel every 30 s, gps.c:2909)
+    ch, nav = gps.synthetic_chans(6, 12, seed=33)
+    ch["prn"][2:, 3] = 0                                   # slot 3 drops out after two blocks
+    ch["prn"][3:, 5] = 31                                  # slot 5 switches satellite at block 3
+    ch["carr_phase"][3, 5] = 0.6180339887
+    ch["prn"][1:3, 7] = 0                                  # slot 7 pauses for two blocks, then resumes
+    ch["carr_phase"][3, 7] = 0.25
+    for ss in (1, 2):
+        want, carr = scenario.oracle_run(ch, nav, ss)
+        with gps.Context(12, 6) as ctx:
+            ctx.set_nav_frames(nav)
+            out, cp = ctx.synth_blocks(ch, ss)
+        assert np.array_equal(out, want)
+        assert np.array_equal(cp, carr)
+
+
+def test_single_block_call_latency_is_far_below_real_time():
+    # the reference's cadence: one 0.1 s block per call
+    import time
+    ch, nav = gps.synthetic_chans(20, 12, seed=8)
+    with gps.Context(12, 1) as ctx:
+        ctx.set_nav_frames(nav)
+        cp = None
+        out = np.empty(gps.BLOCK_ELEMS, np.int8)
+        times = []
+        for b in range(20):
+            one = ch[b:b + 1].copy()
+            if cp is not None:
+                one["carr_phase"][0] = cp
+            t0 = time.perf_counter()
+            _, cp = ctx.synth_blocks(one, 1, out=out)
+            times.append(time.perf_counter() - t0)
+    med = sorted(times[3:])[len(times[3:]) // 2]
+    print("single-block call: median %.2f ms" % (med * 1e3))
+    assert med < 0.05                                      # a block is 100 ms of signal
