@@ -40,7 +40,8 @@ enum {
     GPSB200_ERR_ARG = -1,        /* bad argument (NULL, count, sample size, prn, NAV index) */
     GPSB200_ERR_CUDA = -2,       /* CUDA runtime error; text via gpsb200_last_error() */
     GPSB200_ERR_RANGE = -3,      /* sum of channel amplitudes would overflow the int16 I/Q the reference stores */
-    GPSB200_ERR_NOMEM = -4
+    GPSB200_ERR_NOMEM = -4,
+    GPSB200_ERR_INTERNAL = -5    /* device self-check failed (would mean a bug; never returns wrong samples silently) */
 };
 
 /* One channel for one 0.1 s block: the fields of the reference's channel_t

@@ -122,6 +122,7 @@ struct gpsb200_ctx {
     uint32_t *d_nav = nullptr, *h_nav = nullptr;
     uint32_t *d_chips = nullptr;
     double *d_carr_end = nullptr;
+    int *d_chain_errors = nullptr, *h_chain_errors = nullptr;   // device self-check of the carrier chain
     double *d_guess = nullptr, *h_guess = nullptr;     // speculative block-start phases
     double *d_carr0 = nullptr, *h_carr0 = nullptr;     // exact block-start phases
     CarrierProbe *d_probe = nullptr, *h_probe = nullptr;
@@ -256,6 +257,13 @@ int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int
             chain[c] = st;
         }
     });
+    // fault injection for tests/test_gpu_parity.py::test_chain_self_check_catches_corruption: corrupt one
+    // resolved start phase by one ulp; the device self-check in k_checkpoints must notice
+    if (getenv("GPSB200_FAULT_INJECT_CHAIN") && b1 - b0 > 6 && ctx->h_bc[(size_t) (b0 + 5) * nchan].prn > 0 &&
+        ctx->h_bc[(size_t) (b0 + 4) * nchan].prn == ctx->h_bc[(size_t) (b0 + 5) * nchan].prn) {
+        double &v = ctx->h_carr0[(size_t) (b0 + 5) * ctx->units * nchan];
+        v = bits_f64(f64_bits(v) ^ 1ull);
+    }
     int64_t n = 0;
     for (auto f : fallbacks) n += f;
     return n;
@@ -273,6 +281,7 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.nav = ctx->d_nav;
     a.chipbits = ctx->d_chips;
     a.carr_end = ctx->d_carr_end + off;
+    a.chain_errors = ctx->d_chain_errors;
     a.out = out;
     a.nblk = nblk;
     a.nchan = nchan;
@@ -321,6 +330,7 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     cudaStream_t sp = dst_host ? ctx->s_pre : s;        // stream of the pre-phase
     int rc = upload_nav(ctx, sp);
     if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), sp));
     CU(cudaEventRecord(ctx->ev[0], s));
     int ichunk = 0;
     for (int b0 = 0, b1 = 0; b0 < nblk; b0 = b1, seg_blocks = kSegBlocks) {
@@ -390,6 +400,13 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     ctx->have_last = true;
     if (carr_phase_out)
         for (int c = 0; c < nchan; c++) carr_phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
+    if (dst_host || stats) {
+        CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
+        CU(cudaStreamSynchronize(sp));
+        if (*ctx->h_chain_errors != 0)
+            return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
+                                                      std::to_string(*ctx->h_chain_errors) + " blocks");
+    }
     if (dst_host) {
         CU(cudaStreamSynchronize(s));
         CU(cudaStreamSynchronize(ctx->s_copy));
@@ -519,6 +536,8 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_bc, nbc * sizeof(BlockChanDev), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_ck, nbc * ctx->nruns * sizeof(RunCkpt)));
     CU(cudaMalloc(&ctx->d_carr_end, nbc * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_chain_errors, sizeof(int)));
+    CU(cudaHostAlloc(&ctx->h_chain_errors, sizeof(int), cudaHostAllocDefault));
     const size_t nbu = nbc * ctx->units;
     CU(cudaMalloc(&ctx->d_guess, nbu * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_guess, nbu * sizeof(double), cudaHostAllocDefault));
@@ -555,6 +574,8 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFreeHost(ctx->h_bc);
     cudaFree(ctx->d_ck);
     cudaFree(ctx->d_carr_end);
+    cudaFree(ctx->d_chain_errors);
+    cudaFreeHost(ctx->h_chain_errors);
     cudaFree(ctx->d_guess);
     cudaFreeHost(ctx->h_guess);
     cudaFree(ctx->d_carr0);

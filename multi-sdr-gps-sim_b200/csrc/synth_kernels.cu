@@ -127,7 +127,14 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
         int64_t dummy = 0;
         nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
     }
-    if (a.carr_end && u == a.units - 1) a.carr_end[(size_t) b * a.nchan + c] = x;
+    if (u == a.units - 1) {
+        if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
+        // Self-check of the parallel-in-time chain: the phase this exact walk ends on must BE the
+        // start phase the host resolved for the next block of the same satellite in this launch.
+        if (a.chain_errors && p.prn > 0 && b + 1 < a.nblk && a.bc[(size_t) (b + 1) * a.nchan + c].prn == p.prn &&
+            f64_bits(a.carr0[(size_t) (b + 1) * a.units * a.nchan + c]) != f64_bits(x))
+            atomicAdd(a.chain_errors, 1);
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ struct BlockChanDev {
     double c_carr;     // fl(f_carr * delt)  (gps.c:2821)
     double c_code;     // fl(f_code * delt)  (gps.c:2789)
     double gain;       // gps.c:2756
-    double carr0;      // unused by the kernels (start phases travel in SynthArgs::carr0)
+    double reserved0;  // (start phases travel in SynthArgs::carr0)
     double code0;      // code phase at the first sample (computeCodePhase, gps.c:2049)
     int32_t prn;       // 0 = slot unused
     uint32_t nav0;     // iword | ibit << 8 | icode << 16 at the first sample
@@ -45,7 +45,8 @@ struct SynthArgs {
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
-    double *carr_end;         // [nblk][nchan] carrier phase after the block (diagnostic / chain check)
+    double *carr_end;         // [nblk][nchan] carrier phase after the block
+    int *chain_errors;        // self-check counter: blocks whose walked end phase != the next block's start phase
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
     int units, unit_samples;

@@ -279,3 +279,19 @@ def test_single_block_call_latency_is_far_below_real_time():
     med = sorted(times[3:])[len(times[3:]) // 2]
     print("single-block call: median %.2f ms" % (med * 1e3))
     assert med < 0.05                                      # a block is 100 ms of signal
+
+
+def test_chain_self_check_catches_corruption(monkeypatch):
+    # defence in depth: k_checkpoints re-derives every block's end phase by an exact walk and compares it
+    # with the start phase the host resolved for the next block; a one-ulp corruption must be reported
+    ch, nav = gps.synthetic_chans(12, 32, seed=77)
+    with gps.Context(32, 12) as ctx:
+        ctx.set_nav_frames(nav)
+        good, _ = ctx.synth_blocks(ch, 1)
+        monkeypatch.setenv("GPSB200_FAULT_INJECT_CHAIN", "1")
+        with pytest.raises(gps.GpsB200Error) as e:
+            ctx.synth_blocks(ch, 1)
+        assert e.value.code == -5
+        monkeypatch.delenv("GPSB200_FAULT_INJECT_CHAIN")
+        again, _ = ctx.synth_blocks(ch, 1)
+        assert np.array_equal(good, again)
