@@ -295,3 +295,27 @@ def test_chain_self_check_catches_corruption(monkeypatch):
         monkeypatch.delenv("GPSB200_FAULT_INJECT_CHAIN")
         again, _ = ctx.synth_blocks(ch, 1)
         assert np.array_equal(good, again)
+
+
+def test_full_size_3600s_32ch_device_path_properties():
+    """BASELINE configs[4] at full size on ONE GPU (35 999 blocks x 32 channels = 10.8 Gsamples, 21.6 GB in
+    HBM): the parallel-in-time chain over a whole hour equals the sequential exact chain, and sampled
+    blocks equal the CPU oracle started from sequentially computed phases."""
+    import torch
+    nblk, nchan = 35999, 32
+    ch, nav = gps.synthetic_chans(nblk, nchan, seed=2024)
+    with gps.Context(nchan, nblk) as ctx:
+        ctx.set_nav_frames(nav)
+        dev = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int8, device="cuda")
+        cp, st = ctx.synth_blocks_device(ch, 1, dev.data_ptr(), want_stats=True)
+        torch.cuda.synchronize()
+        assert st.chain_fallbacks < 0.01 * nblk * nchan
+        assert np.array_equal(cp, gps.carrier_chain(ch, threads=16))
+        for b in (20000, 35998):
+            start = ctx.carrier_chain(ch[:b])                 # device chain of the prefix ...
+            assert np.array_equal(start, gps.carrier_chain(ch[:b], threads=16))   # ... equals the host one
+            one = ch[b:b + 1].copy()
+            one["carr_phase"][0] = start
+            want, _ = scenario.oracle_run(one, nav, 1)
+            got = dev[b * gps.BLOCK_ELEMS:(b + 1) * gps.BLOCK_ELEMS].cpu().numpy()
+            assert np.array_equal(got, want), b
