@@ -206,6 +206,8 @@ def test_cli_writes_reference_iqfile_and_stock_compat_file(tmp_path):
     import subprocess
     import zlib
     exe = os.path.join(scenario.ROOT, "multi-sdr-gps-sim_b200", "gpsb200-sim")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(scenario.ROOT, "multi-sdr-gps-sim_b200", "csrc")])
     nav = _nav_file(tmp_path, 12)
     g = scenario.load_golden("sky12_static_10s_i8")
     for extra, keep in (([], list(range(99))), (["--compat-drop"], [0] + list(range(7, 99)))):
