@@ -320,9 +320,9 @@ GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, 
     const double n0 = (double) n;
     double nd = n0;
     int64_t dummy = 0;
-    while (nd > 0.0) {
+    if (m_pos) binade_margins(x, *m_pos, *m_neg);       // start state; later loop-top states were folded in
+    while (nd > 0.0) {                                   // as the previous iteration's post-step state
         double aj;
-        if (m_pos) binade_margins(x, *m_pos, *m_neg);
         const bool wr = walk_iteration<NCO_CARRIER>(x, w, nd, dummy, &aj);
         if (m_pos) {
             binade_margins(aj, *m_pos, *m_neg);
