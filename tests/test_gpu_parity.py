@@ -321,3 +321,36 @@ def test_full_size_3600s_32ch_device_path_properties():
             want, _ = scenario.oracle_run(one, nav, 1)
             got = dev[b * gps.BLOCK_ELEMS:(b + 1) * gps.BLOCK_ELEMS].cpu().numpy()
             assert np.array_equal(got, want), b
+
+
+def test_randomized_differential_vs_oracle():
+    """Seeded differential test: 40 one-block cases with parameters drawn far beyond what a real
+    constellation produces (Doppler to +-30 kHz, tiny gains, code phases and NAV positions at their
+    edges, word/bit roll-over inside the block, several NAV frames, unused slots, int8 and int16)."""
+    rng = np.random.default_rng(20240107)
+    for case in range(40):
+        nchan = int(rng.choice([1, 3, 8, 12, 16, 20, 32]))
+        ss = int(rng.choice([1, 2]))
+        nblk = int(rng.choice([1, 2]))
+        ch, _ = gps.synthetic_chans(nblk, nchan, seed=1000 + case)
+        nframes = 3
+        nav = rng.integers(0, 1 << 32, size=(nframes, nchan, 60), dtype=np.uint32)   # incl. garbage in bits 30..31
+        ch["nav_frame"] = rng.integers(0, nframes, size=(nblk, 1))
+        scale = rng.choice([1.0, 6.0, 0.01, 1e-5])
+        ch["f_carr"] *= scale
+        ch["f_code"] = 1.023e6 + ch["f_carr"] / 1540.0
+        ch["gain"] = rng.uniform(0.0, 1.2, size=ch["gain"].shape) * rng.choice([1.0, 0.02])
+        edge = rng.integers(0, 4, size=nchan)
+        ch["code_phase"][:, edge == 1] = np.nextafter(1023.0, 0)
+        ch["code_phase"][:, edge == 2] = 0.0
+        ch["icode"][:, edge == 3] = 19
+        ch["ibit"][:, edge == 3] = 29                                              # word roll-over inside the block
+        ch["iword"][:, edge == 3] = rng.integers(0, 59)
+        ch["carr_phase"][0] = rng.choice([0.0, np.nextafter(1.0, 0), 0.5, 2.0 ** -40], size=nchan)
+        ch["prn"][:, rng.random(nchan) < 0.15] = 0
+        want, carr = scenario.oracle_run(ch, nav, ss)
+        with gps.Context(nchan, nblk, max_nav_frames=nframes) as ctx:
+            ctx.set_nav_frames(nav)
+            out, cp = ctx.synth_blocks(ch, ss)
+        assert np.array_equal(out, want), (case, nchan, ss, scale)
+        assert np.array_equal(cp, carr), case
