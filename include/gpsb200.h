@@ -158,7 +158,7 @@ int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
  * 1008-1072,2066-2140, allocateChannel gps.c:2142-2235, the 10 Hz / 30 s loop gps.c:2703-2765,
  * 2870-2932). Almanac pages are not generated (reference run with its almanac disabled). */
 typedef struct gpsb200_scenario_config {
-    const char *nav_file;          /* -e: RINEX v2 navigation file */
+    const char *nav_file;          /* -e: RINEX v2 (or, with rinex3, v3) navigation file */
     const char *motion_file;       /* -m: ECEF motion csv "t,x,y,z" at 10 Hz, NULL = static */
     double lat_deg, lon_deg, height_m;   /* -l */
     int32_t duration_ds;           /* -d in 0.1 s units: (int)(seconds*10+0.5) (gps-sim.c:140); blocks = this - 1 */
@@ -166,7 +166,7 @@ typedef struct gpsb200_scenario_config {
     int32_t ionosphere_enable;     /* 1 = reference default (-I clears it) */
     int32_t pluto_gain;            /* 1 = gain x 2 (gps.c:2759-2763) */
     int32_t start_year, start_month, start_day, start_hour, start_min;   /* -s; year 0: first ephemeris epoch */
-    int32_t reserved;
+    int32_t rinex3;                /* -3: nav_file is RINEX v3 (gps.c:1512-1891) instead of v2 */
     double start_sec;
 } gpsb200_scenario_config_t;
 typedef struct gpsb200_scenario gpsb200_scenario_t;

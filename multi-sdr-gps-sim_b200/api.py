@@ -48,7 +48,7 @@ class ScenarioConfig(C.Structure):
                 ("duration_ds", C.c_int32), ("max_chan", C.c_int32), ("ionosphere_enable", C.c_int32),
                 ("pluto_gain", C.c_int32),
                 ("start_year", C.c_int32), ("start_month", C.c_int32), ("start_day", C.c_int32),
-                ("start_hour", C.c_int32), ("start_min", C.c_int32), ("reserved", C.c_int32),
+                ("start_hour", C.c_int32), ("start_min", C.c_int32), ("rinex3", C.c_int32),
                 ("start_sec", C.c_double)]
 
 
@@ -137,7 +137,7 @@ def carrier_chain(chans, phase_in=None, threads=16):
 
 
 def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None, start=None,
-             ionosphere=True, pluto_gain=False):
+             ionosphere=True, pluto_gain=False, rinex3=False):
     """Run the host scenario engine. -> (chans[nblk, max_chan] CHAN_DTYPE, nav[nframes, max_chan, 60] uint32).
     start: (y, m, d, hh, mm, sec) or None for the first ephemeris epoch."""
     cfg = ScenarioConfig()
@@ -148,6 +148,7 @@ def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None,
     cfg.max_chan = max_chan
     cfg.ionosphere_enable = 1 if ionosphere else 0
     cfg.pluto_gain = 1 if pluto_gain else 0
+    cfg.rinex3 = 1 if rinex3 else 0
     if start:
         (cfg.start_year, cfg.start_month, cfg.start_day, cfg.start_hour, cfg.start_min) = [int(v) for v in start[:5]]
         cfg.start_sec = float(start[5])

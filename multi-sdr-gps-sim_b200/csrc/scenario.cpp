@@ -1,7 +1,7 @@
 // Host-side scenario engine: RINEX-2 navigation file + receiver location/motion ->
 // per-block channel parameters (gpsb200_chan_t) and NAV frames, i.e. everything the
 // reference's producer thread computes OUTSIDE its sample loop:
-//   RINEX v2 reader            (reference gps.c:1131-1505)
+//   RINEX v2 / v3 readers      (reference gps.c:1131-1505, 1512-1891)
 //   time / coordinate helpers  (gps.c:315-499, 1094-1124)
 //   satellite position, range, Klobuchar delay (gps.c:508-611, 1893-2026)
 //   code phase / NAV position  (gps.c:2033-2064)
@@ -13,7 +13,7 @@
 // tests/test_scenario.py compares every field with the reference's own dumps.
 //
 // Scope notes: almanac pages are not generated (the reference run with its almanac
-// disabled, as in all BASELINE configs); RINEX v3, downloads, interactive motion and
+// disabled, as in all BASELINE configs); downloads, interactive motion and
 // the HackRF/Pluto specifics (except the Pluto gain doubling) are out of scope.
 #include <cmath>
 #include <cstdio>
@@ -461,6 +461,38 @@ bool label_is(const std::string &line, const char *label) {
     return line.size() > 60 && line.compare(60, strlen(label), label) == 0;
 }
 
+// the seven BROADCAST ORBIT lines of one record; four 19-character fields starting at column c0
+// (3 in RINEX 2, 4 in RINEX 3), plus the derived quantities of gps.c:1489-1493
+void fill_orbit(Eph &e, const std::string l[7], int c0) {
+    e.iode = (int) field(l[0], c0, 19);
+    e.crs = field(l[0], c0 + 19, 19);
+    e.deltan = field(l[0], c0 + 38, 19);
+    e.m0 = field(l[0], c0 + 57, 19);
+    e.cuc = field(l[1], c0, 19);
+    e.ecc = field(l[1], c0 + 19, 19);
+    e.cus = field(l[1], c0 + 38, 19);
+    e.sqrta = field(l[1], c0 + 57, 19);
+    e.toe.sec = field(l[2], c0, 19);
+    e.cic = field(l[2], c0 + 19, 19);
+    e.omg0 = field(l[2], c0 + 38, 19);
+    e.cis = field(l[2], c0 + 57, 19);
+    e.inc0 = field(l[3], c0, 19);
+    e.crc = field(l[3], c0 + 19, 19);
+    e.aop = field(l[3], c0 + 38, 19);
+    e.omgdot = field(l[3], c0 + 57, 19);
+    e.idot = field(l[4], c0, 19);
+    e.toe.week = (int) field(l[4], c0 + 38, 19);
+    e.svh = (int) field(l[5], c0 + 19, 19);
+    if (e.svh > 0 && e.svh < 32) e.svh += 32;
+    e.tgd = field(l[5], c0 + 38, 19);
+    e.iodc = (int) field(l[5], c0 + 57, 19);
+    e.valid = true;
+    e.A = e.sqrta * e.sqrta;
+    e.n = sqrt(kGM / (e.A * e.A * e.A)) + e.deltan;
+    e.sq1e2 = sqrt(1.0 - e.ecc * e.ecc);
+    e.omgkdot = e.omgdot - kOmegaE;
+}
+
 int read_rinex2(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
     FILE *fp = fopen(path, "rt");
     if (!fp) return -1;
@@ -527,33 +559,84 @@ int read_rinex2(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
         bool ok = true;
         for (int k = 0; k < 7 && ok; k++) ok = next(l[k]);
         if (!ok) break;
-        e.iode = (int) field(l[0], 3, 19);
-        e.crs = field(l[0], 22, 19);
-        e.deltan = field(l[0], 41, 19);
-        e.m0 = field(l[0], 60, 19);
-        e.cuc = field(l[1], 3, 19);
-        e.ecc = field(l[1], 22, 19);
-        e.cus = field(l[1], 41, 19);
-        e.sqrta = field(l[1], 60, 19);
-        e.toe.sec = field(l[2], 3, 19);
-        e.cic = field(l[2], 22, 19);
-        e.omg0 = field(l[2], 41, 19);
-        e.cis = field(l[2], 60, 19);
-        e.inc0 = field(l[3], 3, 19);
-        e.crc = field(l[3], 22, 19);
-        e.aop = field(l[3], 41, 19);
-        e.omgdot = field(l[3], 60, 19);
-        e.idot = field(l[4], 3, 19);
-        e.toe.week = (int) field(l[4], 41, 19);
-        e.svh = (int) field(l[5], 22, 19);
-        if (e.svh > 0 && e.svh < 32) e.svh += 32;
-        e.tgd = field(l[5], 41, 19);
-        e.iodc = (int) field(l[5], 60, 19);
-        e.valid = true;
-        e.A = e.sqrta * e.sqrta;
-        e.n = sqrt(kGM / (e.A * e.A * e.A)) + e.deltan;
-        e.sq1e2 = sqrt(1.0 - e.ecc * e.ecc);
-        e.omgkdot = e.omgdot - kOmegaE;
+        fill_orbit(e, l, 3);
+    }
+    fclose(fp);
+    if (g0.week >= 0) ieph += 1;
+    return ieph;
+}
+
+// ---- RINEX v3 navigation reader (gps.c:1512-1891): GPS records only ------------------------------------------
+int read_rinex3(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
+    FILE *fp = fopen(path, "rt");
+    if (!fp) return -1;
+    char buf[256];
+    auto next = [&](std::string &out) -> bool {
+        if (!fgets(buf, 100, fp)) return false;
+        out = buf;
+        return true;
+    };
+    std::string ln;
+    int flags = 0;
+    while (next(ln)) {
+        if (label_is(ln, "COMMENT")) continue;
+        if (label_is(ln, "END OF HEADER")) break;
+        if (label_is(ln, "RINEX VERSION / TYPE")) {
+            if (field(ln, 0, 9) < 3.0 || ln.size() <= 40 || (ln[20] != 'N' && ln[40] != 'G')) {
+                fclose(fp);
+                return -2;
+            }
+        } else if (label_is(ln, "IONOSPHERIC CORR")) {
+            if (ln.compare(0, 4, "GPSA") == 0) {
+                for (int k = 0; k < 4; k++) io.alpha[k] = field(ln, 5 + 12 * k, 12);
+                flags |= 1;
+            } else if (ln.compare(0, 4, "GPSB") == 0) {
+                for (int k = 0; k < 4; k++) io.beta[k] = field(ln, 5 + 12 * k, 12);
+                flags |= 2;
+            }
+        } else if (label_is(ln, "TIME SYSTEM CORR") && ln.compare(0, 4, "GPUT") == 0) {
+            io.A0 = field(ln, 5, 17);
+            io.A1 = field(ln, 22, 16);
+            io.tot = ifield(ln, 38, 7);
+            io.wnt = ifield(ln, 45, 6);
+            if (io.tot % 4096 == 0) flags |= 4;
+        } else if (label_is(ln, "LEAP SECONDS")) {
+            io.dtls = ifield(ln, 0, 6);
+            flags |= 8;
+        }
+    }
+    io.valid = flags == 0xF;
+    GpsTime g0;
+    g0.week = -1;
+    int ieph = 0;
+    while (next(ln)) {
+        if (ln.empty() || ln[0] != 'G') continue;
+        const int sv = ifield(ln, 1, 2) - 1;
+        Date t;
+        t.y = ifield(ln, 4, 4);
+        t.m = ifield(ln, 9, 2);
+        t.d = ifield(ln, 12, 2);
+        t.hh = ifield(ln, 15, 2);
+        t.mm = ifield(ln, 18, 2);
+        t.sec = (double) ifield(ln, 21, 2);
+        if (sv < 0 || sv >= kMaxSat || t.m < 1 || t.m > 12) break;
+        const GpsTime g = date_to_gps(t);
+        if (g0.week == -1) g0 = g;
+        if (gps_diff(g, g0) > kSecHour) {
+            g0 = g;
+            if (++ieph >= kEphSets) break;
+        }
+        Eph &e = eph[ieph][sv];
+        e.t = t;
+        e.toc = g;
+        e.af0 = field(ln, 23, 19);
+        e.af1 = field(ln, 42, 19);
+        e.af2 = field(ln, 61, 19);
+        std::string l[7];
+        bool ok = true;
+        for (int k = 0; k < 7 && ok; k++) ok = next(l[k]);
+        if (!ok) break;
+        fill_orbit(e, l, 4);
     }
     fclose(fp);
     if (g0.week >= 0) ieph += 1;
@@ -587,8 +670,8 @@ int build(gpsb200_scenario *S) {
         for (auto &e : set) e = Eph();
     IonoUtc io;
     io.enable = cfg.ionosphere_enable != 0;
-    const int neph = read_rinex2(cfg.nav_file, eph, io);
-    if (neph <= 0) return fail(S, "cannot read RINEX-2 navigation file (or no ephemeris in it)");
+    const int neph = cfg.rinex3 ? read_rinex3(cfg.nav_file, eph, io) : read_rinex2(cfg.nav_file, eph, io);
+    if (neph <= 0) return fail(S, "cannot read the RINEX navigation file (wrong version flag, or no ephemeris in it)");
 
     // receiver positions per 0.1 s (gps.c:2331-2363, 2489-2500)
     int numd = cfg.duration_ds;

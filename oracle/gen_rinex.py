@@ -96,6 +96,68 @@ def elements(prn, lat_deg, lon_deg):
     return dict(inc=inc, ecc=ecc, sqrta=sqrta, aop=aop, omg0=omg0, m0=m0)
 
 
+def d17(v):
+    """Fortran D17.10 (RINEX 3 TIME SYSTEM CORR a0)."""
+    if v == 0.0:
+        return " 0.0000000000D+00"
+    sgn = "-" if v < 0 else " "
+    a = abs(v)
+    e = int(math.floor(math.log10(a))) + 1
+    ms = "%.10f" % (a / 10.0 ** e)
+    if ms.startswith("1."):
+        e += 1
+        ms = "%.10f" % (a / 10.0 ** e)
+    return "%s%sD%s%02d" % (sgn, ms, "+" if e >= 0 else "-", abs(e))
+
+
+def d16(v):
+    """Fortran D16.9 (RINEX 3 TIME SYSTEM CORR a1)."""
+    if v == 0.0:
+        return " 0.000000000D+00"
+    sgn = "-" if v < 0 else " "
+    a = abs(v)
+    e = int(math.floor(math.log10(a))) + 1
+    ms = "%.9f" % (a / 10.0 ** e)
+    if ms.startswith("1."):
+        e += 1
+        ms = "%.9f" % (a / 10.0 ** e)
+    return "%s%sD%s%02d" % (sgn, ms, "+" if e >= 0 else "-", abs(e))
+
+
+def write3(path, nsat):
+    """RINEX 3 flavour of the same constellation, laid out as readRinex3 parses it
+    (reference gps.c:1512-1891): IONOSPHERIC CORR GPSA/GPSB 4D12.4 at column 5, TIME SYSTEM CORR
+    GPUT D17.10,D16.9,I7,I5, records 'Gnn yyyy mm dd hh mm ss' + 3D19.12, orbit lines 4X,4D19.12."""
+    L = []
+
+    def hdr(body, label):
+        L.append("%-60s%-20s" % (body, label))
+
+    hdr("     3.04           N: GNSS NAV DATA    G: GPS", "RINEX VERSION / TYPE")
+    hdr("gpsb200 gen_rinex   synthetic sky-%-3d   20240107 020000 UTC" % nsat, "PGM / RUN BY / DATE")
+    hdr("GPSA " + d12(1.118e-8) + d12(7.451e-9) + d12(-5.96e-8) + d12(-5.96e-8), "IONOSPHERIC CORR")
+    hdr("GPSB " + d12(9.011e4) + d12(1.638e4) + d12(-1.966e5) + d12(-6.554e4), "IONOSPHERIC CORR")
+    hdr("GPUT " + d17(9.313225746155e-10) + d16(8.881784197001e-16) + "%7d%5d" % (61440, WEEK), "TIME SYSTEM CORR")
+    hdr("%6d" % 18, "LEAP SECONDS")
+    hdr("", "END OF HEADER")
+    for prn, (lat, lon) in zip(range(1, nsat + 1), sub_points(nsat)):
+        el = elements(prn, lat, lon)
+        L.append("G%02d 2024 01 07 02 00 00" % prn + d19(1e-5 * prn) + d19(1e-12 * prn) + d19(0.0))
+        rows = [
+            (float(prn), 10.0 + prn, 4.5e-9, el["m0"]),
+            (1e-6, el["ecc"], 5e-6, el["sqrta"]),
+            (TOE_SOW, 1e-8 * prn, el["omg0"], -1e-8 * prn),
+            (el["inc"], 200.0 + prn, el["aop"], -8e-9),
+            (1e-10, 1.0, float(WEEK), 0.0),
+            (0.0, 0.0, -1e-8, float(prn)),
+            (TOE_SOW - 30.0, 4.0, 0.0, 0.0),
+        ]
+        for r in rows:
+            L.append("    " + "".join(d19(v) for v in r))
+    with open(path, "w") as f:
+        f.write("\n".join(L) + "\n")
+
+
 def write(path, nsat):
     L = []
 
@@ -131,5 +193,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--nsat", type=int, default=12)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--v3", action="store_true", help="write RINEX 3 instead of RINEX 2")
     a = ap.parse_args()
-    write(a.out, a.nsat)
+    (write3 if a.v3 else write)(a.out, a.nsat)

@@ -161,6 +161,7 @@ int main(int argc, char **argv) {
             sscanf(argv[++i], "%d/%d/%d,%d:%d:%lf", &sim.start.y, &sim.start.m, &sim.start.d,
                    &sim.start.hh, &sim.start.mm, &sim.start.sec);
         else if (!strcmp(argv[i], "--iq16")) sim.sample_size = SC16;
+        else if (!strcmp(argv[i], "-3")) sim.use_rinex3 = true;
         else if (!strcmp(argv[i], "--pluto-gain")) sim.sdr_type = SDR_PLUTOSDR;
         else if (!strcmp(argv[i], "--iq") && i + 1 < argc) iq_name = argv[++i];
         else if (!strcmp(argv[i], "--params") && i + 1 < argc) par_name = argv[++i];

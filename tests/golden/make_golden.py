@@ -40,6 +40,8 @@ SCENARIOS = {
     "sky32_static_10s_i8": (32, "ref_dump32", 10, [], [0]),
     # BASELINE configs[3]: motion file + --iq16 + 60 s; digests only (parameters come from the scenario engine)
     "sky12_track_60s_i16": (12, "ref_dump12", 60, ["--iq16", "-m", "@MOTION"], []),
+    # the same constellation written as RINEX 3 and read by the reference's readRinex3 (-3)
+    "sky12_rinex3_3s_i8": (12, "ref_dump12", 3, ["-3"], []),
 }
 
 
@@ -48,7 +50,7 @@ def run(name):
     with tempfile.TemporaryDirectory() as td:
         nav = os.path.join(td, "sky.nav")
         subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "gen_rinex.py"),
-                               "--nsat", str(nsat), "--out", nav])
+                               "--nsat", str(nsat), "--out", nav] + (["--v3"] if "-3" in extra else []))
         iq, par = os.path.join(td, "iq.bin"), os.path.join(td, "p.bin")
         if "@MOTION" in extra:
             mot = os.path.join(td, "track.csv")

@@ -17,13 +17,14 @@ CASES = {
     "sky12_static_35s_i8": dict(nsat=12, chan=12, secs=35),
     "sky32_static_10s_i8": dict(nsat=32, chan=32, secs=10),
     "sky12_circle_10s_i16": dict(nsat=12, chan=12, secs=10, motion=True),
+    "sky12_rinex3_3s_i8": dict(nsat=12, chan=12, secs=3, v3=True),
 }
 
 
-def make_nav(tmp_path, nsat):
+def make_nav(tmp_path, nsat, v3=False):
     nav = tmp_path / ("sky%d.nav" % nsat)
     subprocess.check_call([sys.executable, os.path.join(scenario.ROOT, "oracle", "gen_rinex.py"),
-                           "--nsat", str(nsat), "--out", str(nav)])
+                           "--nsat", str(nsat), "--out", str(nav)] + (["--v3"] if v3 else []))
     return str(nav)
 
 
@@ -42,8 +43,8 @@ def test_scenario_engine_matches_reference_dump_bit_for_bit(name, tmp_path):
     g = scenario.load_golden(name)
     want, frames = scenario.golden_chans(g)
     mot = motion_file(tmp_path) if c.get("motion") else None
-    got, nav = gps.scenario(make_nav(tmp_path, c["nsat"]), *LOC, seconds=c["secs"], max_chan=c["chan"],
-                            motion_file=mot, start=START)
+    got, nav = gps.scenario(make_nav(tmp_path, c["nsat"], c.get("v3", False)), *LOC, seconds=c["secs"],
+                            max_chan=c["chan"], motion_file=mot, start=START, rinex3=c.get("v3", False))
     assert got.shape == want.shape
     assert np.array_equal(got["prn"], want["prn"])
     act = want["prn"] > 0
@@ -67,3 +68,10 @@ def test_scenario_engine_matches_reference_dump_bit_for_bit(name, tmp_path):
 def test_scenario_errors():
     with pytest.raises(gps.GpsB200Error):
         gps.scenario("/nonexistent.nav", *LOC, seconds=5)
+
+
+def test_rinex_version_flag_must_match_the_file(tmp_path):
+    with pytest.raises(gps.GpsB200Error):
+        gps.scenario(make_nav(tmp_path, 12, v3=True), *LOC, seconds=3, start=START)            # v3 file, v2 reader
+    with pytest.raises(gps.GpsB200Error):
+        gps.scenario(make_nav(tmp_path, 12), *LOC, seconds=3, start=START, rinex3=True)         # v2 file, v3 reader

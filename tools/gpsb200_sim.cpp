@@ -15,7 +15,7 @@
 
 static void usage() {
     fprintf(stderr,
-            "gpsb200-sim -e NAV -l lat,lon,h [-d SEC] [-m motion.csv] [-s y/m/d,h:m:s] [--iq16] [-I]\n"
+            "gpsb200-sim -e NAV [-3] -l lat,lon,h [-d SEC] [-m motion.csv] [-s y/m/d,h:m:s] [--iq16] [-I]\n"
             "            [--chan N] [-o iqdata.bin] [--compat-drop]\n");
     exit(2);
 }
@@ -43,6 +43,7 @@ int main(int argc, char **argv) {
                    &sc.start_min, &sc.start_sec);
         else if (a == "--iq16") sample_size = GPSB200_SC16;
         else if (a == "-I") sc.ionosphere_enable = 0;
+        else if (a == "-3") sc.rinex3 = 1;
         else if (a == "--chan") sc.max_chan = atoi(need());
         else if (a == "-o") out = need();
         else if (a == "--compat-drop") compat = true;
