@@ -1,12 +1,13 @@
-// C ABI of libgpsb200.so (include/gpsb200.h): context, host-side exact carrier chain,
-// parameter upload, kernel launches, result download.
+// C ABI of libgpsb200.so (include/gpsb200.h): context, pipeline, host share of the carrier chain.
 //
-// Host work per block and channel is what the reference's 10 Hz path hands to its
-// sample loop (gps.c:2731-2765) plus ONE thing the loop carries implicitly: the
-// carrier phase at the start of the block, which in the reference is simply
-// whatever 300000 sequential FP64 additions left behind (gps.c:2821-2826). Here it
-// is produced by the exact fast-forward of nco_exact.h, one host thread per group
-// of channels, running ahead of the GPU batch by batch.
+// Host work per block and channel is what the reference's 10 Hz path hands to its sample loop
+// (gps.c:2731-2765) plus ONE thing the loop carries implicitly: the carrier phase at the start
+// of the block, which in the reference is whatever 300000 sequential FP64 additions left behind
+// (gps.c:2821-2826). That chain is resolved parallel in time (nco_exact.h): the host GUESSES
+// every block's start phase, k_probe walks every block from its guess on the GPU, and a cheap
+// sequential host scan (carrier_fixup) turns the probes into exact start phases -- falling back to
+// the exact sequential walk for the rare block whose probe cannot be used. Then k_checkpoints and
+// k_synth run, in chunks whose download overlaps the synthesis of later chunks.
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -16,10 +16,10 @@
 //                   channels). LANE = CHANNEL: every lane steps its channel's two
 //                   FP64 NCOs sample by sample with the reference's own rounding
 //                   (__dadd_rn), looks up the gain-scaled carrier table and the
-//                   chip sign in shared memory, and the warp adds the channels
-//                   with one REDUX.SUM (packed I + Q<<16). Sums are staged in
-//                   shared memory and written out 32 samples at a time as
-//                   coalesced int8/int16 I/Q.
+//                   chip sign (from a per-lane register window of the packed C/A code),
+//                   and the warp adds the channels with one REDUX.SUM (packed
+//                   I + Q<<16). Sums are staged in shared memory and written out 64
+//                   samples at a time as coalesced int8/int16 I/Q.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
