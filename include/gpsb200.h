@@ -56,8 +56,8 @@ typedef struct gpsb200_chan {
     int32_t icode;        /* code period in bit 0..19 (gps.c:2058) */
     int32_t nav_frame;    /* which NAV frame (set of 60 words) this block uses, see gpsb200_set_nav */
     int32_t reserved;
-    double f_carr;        /* Hz, Doppler (gps.c:2043) */
-    double f_code;        /* Hz (gps.c:2044) */
+    double f_carr;        /* Hz, Doppler (gps.c:2043); |f_carr| < 2.9 MHz */
+    double f_code;        /* Hz (gps.c:2044); 0 < f_code <= 1.07 MHz */
     double carr_phase;    /* cycles in [0,1): used for the first block of a call and whenever prn differs
                              from the previous block's prn in the same slot (allocateChannel, gps.c:2203-2210);
                              otherwise the phase is carried from the previous block (gps.c:2821-2826) */

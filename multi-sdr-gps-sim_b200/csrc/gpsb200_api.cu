@@ -177,8 +177,11 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 }
                 if (in.prn > 32 || in.iword < 0 || in.iword >= GPSB200_NAV_WORDS || in.ibit < 0 || in.ibit >= 30 ||
                     in.icode < 0 || in.icode >= 20 || in.nav_frame < 0 || in.nav_frame >= ctx->cfg.max_nav_frames ||
-                    !(in.code_phase >= 0.0 && in.code_phase < 1023.0) || !(in.f_code > 0.0) ||
-                    !std::isfinite(in.f_carr) || !std::isfinite(in.gain)) {
+                    !(in.code_phase >= 0.0 && in.code_phase < 1023.0) ||
+                    // the per-lane chip window holds 24 chips per 64 samples: f_code <= 1.07 MHz (GPS: 1.023 MHz +- 4 Hz)
+                    !(in.f_code > 0.0 && in.f_code <= 1.07e6) ||
+                    // one wrap per step keeps the phase in [0,1) only for |f_carr * delt| < 1
+                    !(std::isfinite(in.f_carr) && std::fabs(in.f_carr) < 2.9e6) || !std::isfinite(in.gain)) {
                     status[c] = GPSB200_ERR_ARG;
                     return;
                 }

@@ -145,6 +145,12 @@ def test_errors_are_loud():
         assert e.value.code == -1
         with pytest.raises(gps.GpsB200Error):
             ctx.synth_blocks(np.concatenate([ch, ch]), 1)      # nblk > max_blocks
+        for field, val in (("f_code", 2.0e6), ("f_carr", 3.1e6), ("f_carr", float("nan"))):
+            bad = ch.copy()
+            bad[field][0, 1] = val
+            with pytest.raises(gps.GpsB200Error) as e:
+                ctx.synth_blocks(bad, 1)
+            assert e.value.code == -1
 
 
 def test_full_size_300s_32ch_int8_properties():
