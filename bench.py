@@ -51,44 +51,97 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    NVML in-process every 5 ms (the timed region of the resident run is ~20 ms per step, far
+    shorter than one `nvidia-smi` start-up); `nvidia-smi -lms` is the fallback when NVML cannot
+    be loaded. Started before the warm-up steps so that it is running when the timed region opens;
+    only samples whose time stamp falls inside the region are reported."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, uuid=None):
+        self.rows = []            # (time, sm_mhz, set(reasons))
+        self.max_mhz = None
+        self.mode = None
         self.proc = None
+        self._stop = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[index]) if index < len(ids) else index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv, self.h, self.mode = nv, h, "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.mode = "nvidia-smi"
+            self.t = threading.Thread(target=self._pump_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
+    def _poll_nvml(self):
+        nv, h = self.nv, self.h
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"),
+                (nv.nvmlClocksEventReasonHwPowerBrakeSlowdown, "hw_power_brake")]
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append((time.time(), mhz, {nm for b, nm in bits if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def _pump_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                mhz = float(r[0])
+                self.max_mhz = max(self.max_mhz or 0.0, float(r[1]))
+            except Exception:
+                continue
+            rs = {nm for k, nm in enumerate(names) if len(r) > 4 + k and r[4 + k].lower().startswith("active")}
+            self.rows.append((time.time(), mhz, rs))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.1 <= t <= t1 + 0.3] or [r for (_, r) in self.rows]
-        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = set()
-        for r in rows:
-            for k, nm in enumerate(names):
-                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if self.mode == "nvidia-smi":
+            time.sleep(0.15)
+            self.proc.terminate()
+        self._stop.set()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        where = "timed region"
+        if not inside:                      # region shorter than the sampling period: nearest samples under load
+            inside = [r for r in self.rows if t0 - 0.25 <= r[0] <= t1 + 0.05]
+            where = "timed region +-0.25 s (warm-up load)"
+        sm = [r[1] for r in inside]
+        reasons = sorted(set().union(*[r[2] for r in inside])) if inside else []
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside), "source": self.mode, "window": where}
 
 
 def host_cpus():
@@ -251,10 +304,14 @@ def main():
     # ---- resident-input run: parameters + carrier chain uploaded once, kernels replayed ----
     ctx.synth_blocks_device(chans, ss, out_dev.data_ptr(), stream=sh)
     torch.cuda.synchronize()
+    sampler = None
+    if rank == 0:
+        uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
+        sampler = ClockSampler(local, uuid)
     for _ in range(args.warmup):
         ctx.replay_device(out_dev.data_ptr(), sh, 7)
+    torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     t_wall0 = time.time()
     ev[0].record(stream)
@@ -265,6 +322,7 @@ def main():
         ev[3 * i + 2].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 2)      # per-sample synthesis
         ev[3 * i + 3].record(stream)
+    torch.cuda.synchronize()
     barrier()
     t_wall1 = time.time()
     total_ms = ev[0].elapsed_time(ev[3 * args.steps])

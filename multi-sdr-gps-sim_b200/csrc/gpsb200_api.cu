@@ -382,8 +382,10 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
             CU(launch_synth(a, s));
             st.launches += 1;
         } else {
-            for (int c0 = b0; c0 < b1; c0 += kSynthChunk, ichunk++) {
-                const int nc = std::min(kSynthChunk, b1 - c0);
+            // the very first chunks are short, so that the download (the long pole of this path) starts early
+            for (int c0 = b0, nc = 0; c0 < b1; c0 += nc, ichunk++) {
+                nc = c0 == 0 ? 32 : (c0 == 32 ? 96 : (c0 == 128 ? 128 : kSynthChunk));
+                nc = std::min(nc, b1 - c0);
                 SynthArgs ac{};
                 char *dout = (char *) dst_dev + (size_t) c0 * blk_bytes;
                 fill_args(ctx, ac, c0, nc, nchan, sample_size, dout);
@@ -532,7 +534,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_pre, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
-    const int nchunk = (c.max_blocks + kSynthChunk - 1) / kSynthChunk + (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 2;
+    const int nchunk = (c.max_blocks + kSynthChunk - 1) / kSynthChunk + (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 5;
     ctx->ev_done.resize(nchunk);
     for (auto &e : ctx->ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const size_t nbc = (size_t) c.max_blocks * c.max_chan;

@@ -149,7 +149,7 @@ struct SynthSmem {
     int32_t atab[kAtabRows][32];                 // [k][lane]: I + (Q << 16), gain-scaled (gps.c:2781-2782)
     uint32_t cabits[kChipWords][GROUP];          // [word][channel]: C/A chips, bit n = ca[n mod 1023], n < 1056
     uint32_t nav[kNavWords][GROUP];              // NAV words of this block's frame
-    int32_t stage[kMaxWarps][kChunkMax * (32 / GROUP)]; // per-warp staging of one chunk of samples per run
+    alignas(16) int32_t stage[kMaxWarps][kChunkMax * (32 / GROUP)]; // per-warp staging of one chunk of samples per run
 };
 
 template <int GROUP>
@@ -292,14 +292,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         uint32_t w8 = (__funnelshift_r(lo, hi, j0 & 31) ^ (dbit ? 0xFFFFFFFFu : 0u)) << 8;
         double KY = K52 - (double) j0;
         // table lookup + channel sum of one sample from a VALID (wrapped) NCO state
-        auto emit = [&](double xs, double ys, int i) {
+        auto emit = [&](double xs, double ys) -> int {
             const int k = __double2loint(__dadd_rz(xs, K43));  // (int) floor(carr_phase*512), gps.c:2775
             const int rel = __double2loint(__dadd_rz(ys, KY)); // (int) code_phase - j0, gps.c:2817
             const int kk = k ^ ((w8 >> rel) & 0x100);          // dataBit*codeCA == -1  <=>  k += 256 (mod 512)
             int e;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(abase + (uint32_t) kk * 128u));
-            const int sum = group_sum<GROUP>(e);               // gps.c:2785-2786 over channels
-            stage[sub * kChunkMax + i] = sum;                  // every lane of the group stores the same word
+            return group_sum<GROUP>(e);                        // gps.c:2785-2786 over channels
+        };
+        // four sums at a time go to the staging row (one 16-byte store; every lane of the group
+        // stores the same words)
+        auto park = [&](int i, int s0_, int s1_, int s2_, int s3_) {
+            *reinterpret_cast<int4 *>(&stage[sub * kChunkMax + i]) = make_int4(s0_, s1_, s2_, s3_);
         };
         // one reference step with its wrap / NAV-bit bookkeeping (gps.c:2789-2826)
         auto step_checked = [&](double &xs, double &ys) {
@@ -336,23 +340,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
             const bool risky = (hx >= thr_x_hi) | (hx <= thr_x_lo) | (hy >= thr_y);
             if (!__any_sync(0xFFFFFFFFu, risky)) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    emit(x, y, g8 + i);
-                    x = __dadd_rn(x, cc);                      // gps.c:2821, no wrap possible
-                    y = __dadd_rn(y, dd);                      // gps.c:2789, no wrap possible
+                for (int h = 0; h < 8; h += 4) {
+                    int sv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        sv[i] = emit(x, y);
+                        x = __dadd_rn(x, cc);                  // gps.c:2821, no wrap possible
+                        y = __dadd_rn(y, dd);                  // gps.c:2789, no wrap possible
+                    }
+                    park(g8 + h, sv[0], sv[1], sv[2], sv[3]);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    emit(x, y, g8 + i);
-                    const double xn = __dadd_rn(x, cc), yn = __dadd_rn(y, dd);
-                    const bool wrap = ((unsigned) __double2hiint(xn) >= 0x3FF00000u) |
-                                      ((unsigned) __double2hiint(yn) >= 0x408FF800u);
-                    if (__any_sync(0xFFFFFFFFu, wrap)) step_checked(x, y);
-                    else {
-                        x = xn;
-                        y = yn;
+                for (int h = 0; h < 8; h += 4) {
+                    int sv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        sv[i] = emit(x, y);
+                        const double xn = __dadd_rn(x, cc), yn = __dadd_rn(y, dd);
+                        const bool wrap = ((unsigned) __double2hiint(xn) >= 0x3FF00000u) |
+                                          ((unsigned) __double2hiint(yn) >= 0x408FF800u);
+                        if (__any_sync(0xFFFFFFFFu, wrap)) step_checked(x, y);
+                        else {
+                            x = xn;
+                            y = yn;
+                        }
                     }
+                    park(g8 + h, sv[0], sv[1], sv[2], sv[3]);
                 }
             }
         }
