@@ -130,6 +130,7 @@ struct gpsb200_ctx {
     void *d_out = nullptr;
     size_t out_bytes = 0;
     bool nav_dirty = true;
+    bool graded_chunks = true;             // GPSB200_GRADED_CHUNKS=0: uniform 256-block chunks (A/B knob)
     std::unique_ptr<WorkerPool> pool;      // host passes (guesses, fix-up scan)
     SynthArgs last{};                      // replay state
     bool have_last = false;
@@ -384,7 +385,8 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         } else {
             // the very first chunks are short, so that the download (the long pole of this path) starts early
             for (int c0 = b0, nc = 0; c0 < b1; c0 += nc, ichunk++) {
-                nc = c0 == 0 ? 32 : (c0 == 32 ? 96 : (c0 == 128 ? 128 : kSynthChunk));
+                nc = kSynthChunk;
+                if (ctx->graded_chunks) nc = c0 == 0 ? 32 : (c0 == 32 ? 96 : (c0 == 128 ? 128 : kSynthChunk));
                 nc = std::min(nc, b1 - c0);
                 SynthArgs ac{};
                 char *dout = (char *) dst_dev + (size_t) c0 * blk_bytes;
@@ -524,6 +526,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
             ctx->unit_samples = GPSB200_BLOCK_SAMPLES / u;
         }
     }
+    if (const char *ev = getenv("GPSB200_GRADED_CHUNKS")) ctx->graded_chunks = atoi(ev) != 0;
     ctx->pool.reset(new WorkerPool(std::min(c.host_threads, c.max_chan)));
     *out = ctx;   // from here on errors are reported through the context
     int ndev = 0;
