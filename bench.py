@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS_300S)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of the finished slices")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node (A/B)")
     ap.add_argument("--run-samples", type=int, default=0, help="device work unit (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,6 +265,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gpsb200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # the rank's threads and its page-locked result buffer go to the NUMA node of its GPU (library helper)
+    numa_node = None if args.no_numa_bind else gps.bind_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -395,7 +398,7 @@ def main():
                     "ms_per_step": round(e2e_s * 1e3, 2), "steps": e2e_steps,
                     "ms_best_step_rank0": round(min(e2e_each) * 1e3, 2), "host_chain_ms": round(stats.host_chain_ms, 2),
                     "chain_fallbacks": int(stats.chain_fallbacks), "kernel_launches_per_step": int(stats.launches),
-                    "host_threads": host_threads, "timing": "wall clock around the blocking call, max over ranks",
+                    "host_threads": host_threads, "numa_node": numa_node, "timing": "wall clock around the blocking call, max over ranks",
                     "output_equals_resident_run": same},
             "slice_seed_s": round(t_seed, 3),
         }

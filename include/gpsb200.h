@@ -91,6 +91,14 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx);
 const char *gpsb200_last_error(const gpsb200_ctx_t *ctx);
 const char *gpsb200_version(void);
 
+/* Deployment helper, the counterpart of the reference's thread_to_core() (gps-sim.c:251-262, called by
+ * gps_thread_ep, gps.c:2377): bind the CALLING thread (and every thread it creates afterwards: the
+ * context's host workers, the iqfile writer) to the CPUs of the NUMA node the CUDA device `device`
+ * hangs off, so that page-locked result buffers allocated afterwards (fifo_create, cudaHostAlloc) are
+ * local to the GPU's PCIe root. Call before gpsb200_create / fifo_create. Returns the NUMA node (>= 0),
+ * -1 when the platform reports none (nothing changed), or GPSB200_ERR_CUDA. */
+int gpsb200_bind_numa(int device);
+
 /* NAV words of one channel for one 30 s frame: channel_t.dwrd (gps.h:227) as
  * built by generateNavMsg (gps.c:2066-2140); only bits 29..0 are used
  * (gps.c:2812). Copied; may be updated between synth calls. */

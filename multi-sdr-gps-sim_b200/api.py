@@ -65,7 +65,7 @@ _lib = None
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
-           "gpsb200_codegen",
+           "gpsb200_codegen", "gpsb200_bind_numa",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
            "gpsb200_scenario_chans", "gpsb200_scenario_nav",
@@ -109,6 +109,14 @@ def lib():
         L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
+
+
+def bind_numa(device=0):
+    """gpsb200_bind_numa: pin the calling thread (and threads created later) to the GPU's NUMA node. -> node or -1."""
+    L = lib()
+    L.gpsb200_bind_numa.argtypes = [C.c_int]
+    L.gpsb200_bind_numa.restype = C.c_int
+    return int(L.gpsb200_bind_numa(int(device)))
 
 
 def codegen(prn):

@@ -9,6 +9,7 @@
 // the exact sequential walk for the rare block whose probe cannot be used. Then k_checkpoints and
 // k_synth run, in chunks whose download overlaps the synthesis of later chunks.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -16,6 +17,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -444,6 +446,45 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
 extern "C" {
 
 const char *gpsb200_version(void) { return "gpsb200 0.2 (sm_100a)"; }
+
+int gpsb200_bind_numa(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int) sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return GPSB200_ERR_CUDA;
+    }
+    for (char *p = bus; *p; ++p) *p = (char) tolower((unsigned char) *p);
+    int node = -1;
+    if (FILE *f = fopen((std::string("/sys/bus/pci/devices/") + bus + "/numa_node").c_str(), "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0) return -1;
+    char list[4096] = {0};
+    FILE *f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
+    if (!f) return -1;
+    const bool got = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!got) return -1;
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return -1;
+    int picked = 0;
+    for (const char *p = list; *p && *p != '\n';) {            // "0-31,64-95"
+        char *end = nullptr;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') b = strtol(end + 1, &end, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET((int) c, &cur)) {
+                CPU_SET((int) c, &want);
+                ++picked;
+            }
+        p = *end == ',' ? end + 1 : end;
+    }
+    if (picked == 0 || sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+    return node;
+}
 
 const char *gpsb200_last_error(const gpsb200_ctx_t *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 

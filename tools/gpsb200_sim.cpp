@@ -68,6 +68,7 @@ int main(int argc, char **argv) {
     cfg.max_blocks = batch;
     cfg.max_nav_frames = nframes;
     gpsb200_ctx_t *ctx = nullptr;
+    gpsb200_bind_numa(cfg.device);      // threads and pinned FIFO buffers next to the GPU (cf. thread_to_core, gps.c:2377)
     if (gpsb200_create(&cfg, &ctx) != GPSB200_OK) {
         fprintf(stderr, "gpsb200: %s\n", gpsb200_last_error(ctx));
         return 1;
