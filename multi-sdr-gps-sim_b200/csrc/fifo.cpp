@@ -63,6 +63,8 @@ void free_list(iq_buf *h) {
     }
 }
 
+iq_buf *g_partial = nullptr;          // buffer being filled by gpsb200_fifo_push across calls
+
 std::thread g_writer;
 std::atomic<bool> g_writer_exit{false};
 std::string g_path;
@@ -101,7 +103,11 @@ void fifo_destroy(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     free_list(g_head);
     free_list(g_freelist);
-    g_head = g_tail = g_freelist = nullptr;
+    if (g_partial) {
+        g_partial->next = nullptr;
+        free_list(g_partial);
+    }
+    g_head = g_tail = g_freelist = g_partial = nullptr;
 }
 
 void fifo_wait_next(void) {
@@ -193,8 +199,6 @@ void fifo_release(struct iq_buf *buf) {
 // blocks: the reference keeps filling one acquired buffer across block boundaries and enqueues
 // it whenever it is full. Same behaviour for a contiguous stream of elements; the partly
 // filled buffer is kept for the next call (or flushed by fifo_push_flush at the end).
-static iq_buf *g_partial = nullptr;
-
 int gpsb200_fifo_push(const void *elems, size_t count, int sample_size) {
     const char *src = (const char *) elems;
     const size_t es = sample_size == GPSB200_SC16 ? 2 : 1;

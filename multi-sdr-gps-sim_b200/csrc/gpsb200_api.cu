@@ -382,6 +382,10 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         st.h2d_bytes += (int64_t) (cnt * sizeof(BlockChanDev) + cntu * 2 * sizeof(double));
         st.d2h_bytes += (int64_t) (cntu * sizeof(CarrierProbe));
         if (!dst_host) {
+            // self-check result of k_checkpoints: fetched BEFORE the synthesis launch in stream order, so that the
+            // host can look at it without waiting for the synthesis itself
+            CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(ctx->ev[6], s));
             CU(launch_synth(a, s));
             st.launches += 1;
         } else {
@@ -410,13 +414,16 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     ctx->have_last = true;
     if (carr_phase_out)
         for (int c = 0; c < nchan; c++) carr_phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
-    if (dst_host || stats) {
+    // the device self-check of the carrier chain is never skipped: a wrong start phase must not produce samples silently
+    if (dst_host) {
         CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
         CU(cudaStreamSynchronize(sp));
-        if (*ctx->h_chain_errors != 0)
-            return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
-                                                      std::to_string(*ctx->h_chain_errors) + " blocks");
+    } else {
+        CU(cudaEventSynchronize(ctx->ev[6]));
     }
+    if (*ctx->h_chain_errors != 0)
+        return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
+                                                  std::to_string(*ctx->h_chain_errors) + " blocks");
     if (dst_host) {
         CU(cudaStreamSynchronize(s));
         CU(cudaStreamSynchronize(ctx->s_copy));

@@ -300,6 +300,12 @@ def test_chain_self_check_catches_corruption(monkeypatch):
         with pytest.raises(gps.GpsB200Error) as e:
             ctx.synth_blocks(ch, 1)
         assert e.value.code == -5
+        # the device-destination path reports it as well, with or without a stats request
+        import torch
+        dev = torch.empty(12 * gps.BLOCK_ELEMS, dtype=torch.int8, device="cuda")
+        with pytest.raises(gps.GpsB200Error) as e:
+            ctx.synth_blocks_device(ch, 1, dev.data_ptr())
+        assert e.value.code == -5
         monkeypatch.delenv("GPSB200_FAULT_INJECT_CHAIN")
         again, _ = ctx.synth_blocks(ch, 1)
         assert np.array_equal(good, again)
