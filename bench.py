@@ -312,26 +312,29 @@ def main():
         uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
         sampler = ClockSampler(local, uuid)
     for _ in range(args.warmup):
-        ctx.replay_device(out_dev.data_ptr(), sh, 7)
+        ctx.replay_device(out_dev.data_ptr(), sh, 15)
     torch.cuda.synchronize()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps + 1)]
     t_wall0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
+        ctx.replay_device(out_dev.data_ptr(), sh, 8)      # gain-scaled carrier tables of every block
+        ev[4 * i + 1].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 4)      # speculative carrier probe
-        ev[3 * i + 1].record(stream)
+        ev[4 * i + 2].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 1)      # run checkpoints (exact NCO fast-forward)
-        ev[3 * i + 2].record(stream)
+        ev[4 * i + 3].record(stream)
         ctx.replay_device(out_dev.data_ptr(), sh, 2)      # per-sample synthesis
-        ev[3 * i + 3].record(stream)
+        ev[4 * i + 4].record(stream)
     torch.cuda.synchronize()
     barrier()
     t_wall1 = time.time()
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
-    pr_ms = sum((ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))) / args.steps
-    ck_ms = sum((ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))) / args.steps
-    syn_ms = sum((ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(args.steps))) / args.steps
+    total_ms = ev[0].elapsed_time(ev[4 * args.steps])
+    tb_ms = sum((ev[4 * i].elapsed_time(ev[4 * i + 1]) for i in range(args.steps))) / args.steps
+    pr_ms = sum((ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps))) / args.steps
+    ck_ms = sum((ev[4 * i + 2].elapsed_time(ev[4 * i + 3]) for i in range(args.steps))) / args.steps
+    syn_ms = sum((ev[4 * i + 3].elapsed_time(ev[4 * i + 4]) for i in range(args.steps))) / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
@@ -382,8 +385,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 NCO / int32 accumulate / %s out" % ("int16" if args.iq16 else "int8"),
             "data": "synthetic", "config": workload_config(nchan, args.iq16, world),
-            "clocks": clocks, "gpu_launches": 3 * args.steps,
-            "kernels": {"k_probe_ms": round(pr_ms, 3), "k_checkpoints_ms": round(ck_ms, 3),
+            "clocks": clocks, "gpu_launches": 4 * args.steps,
+            "kernels": {"k_tables_ms": round(tb_ms, 3), "k_probe_ms": round(pr_ms, 3), "k_checkpoints_ms": round(ck_ms, 3),
                         "k_synth_ms": round(syn_ms, 3)},
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),

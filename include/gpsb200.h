@@ -126,7 +126,7 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
 
 /* Re-run the device part of the previous gpsb200_synth_blocks_device call (parameters,
  * start phases and guesses already resident in HBM): used by bench.py to time the kernels
- * alone. kernel_mask bits: 4 = carrier probe, 1 = run checkpoints, 2 = synthesis. */
+ * alone. kernel_mask bits: 8 = carrier tables, 4 = carrier probe, 1 = run checkpoints, 2 = synthesis. */
 int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream, int kernel_mask);
 
 /* Exact carrier phase after n samples of Doppler f_carr (the chain of gps.c:2821-2826

@@ -257,5 +257,5 @@ class Context:
                                                        None if pin is None else pin.ctypes.data, out.ctypes.data))
         return out
 
-    def replay_device(self, dst_ptr=0, stream=0, kernel_mask=7):
+    def replay_device(self, dst_ptr=0, stream=0, kernel_mask=15):
         self._check(lib().gpsb200_replay_device(self._h, C.c_void_p(dst_ptr), C.c_void_p(stream), kernel_mask))

@@ -124,6 +124,7 @@ struct gpsb200_ctx {
     RunCkpt *d_ck = nullptr;
     uint32_t *d_nav = nullptr, *h_nav = nullptr;
     uint32_t *d_chips = nullptr;
+    int32_t *d_atab = nullptr;             // per-block carrier tables (k_tables -> k_synth)
     double *d_carr_end = nullptr;
     int *d_chain_errors = nullptr, *h_chain_errors = nullptr;   // device self-check of the carrier chain
     double *d_guess = nullptr, *h_guess = nullptr;     // speculative block-start phases
@@ -287,6 +288,7 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.ck = ctx->d_ck + off * ctx->nruns;
     a.nav = ctx->d_nav;
     a.chipbits = ctx->d_chips;
+    a.atab = ctx->d_atab + (size_t) blk0 * kAtabRows * 32;
     a.carr_end = ctx->d_carr_end + off;
     a.chain_errors = ctx->d_chain_errors;
     a.out = out;
@@ -360,6 +362,7 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         CU(cudaMemcpyAsync(ctx->d_guess + offu, ctx->h_guess + offu, cntu * sizeof(double), cudaMemcpyHostToDevice, sp));
         SynthArgs a{};
         fill_args(ctx, a, b0, nb, nchan, sample_size, (char *) dst_dev + (size_t) b0 * blk_bytes);
+        CU(launch_tables(a, sp));                        // needs only the parameters: off the chain's critical path
         if (b0 == 0) CU(cudaEventRecord(ctx->ev[1], sp));
         CU(launch_probe(a, sp));
         if (b0 == 0) CU(cudaEventRecord(ctx->ev[2], sp));
@@ -378,7 +381,7 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
             CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
             ichunk++;
         }
-        st.launches += 2;
+        st.launches += 3;
         st.h2d_bytes += (int64_t) (cnt * sizeof(BlockChanDev) + cntu * 2 * sizeof(double));
         st.d2h_bytes += (int64_t) (cntu * sizeof(CarrierProbe));
         if (!dst_host) {
@@ -593,6 +596,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_bc, nbc * sizeof(BlockChanDev), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_ck, nbc * ctx->nruns * sizeof(RunCkpt)));
     CU(cudaMalloc(&ctx->d_carr_end, nbc * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_atab, (size_t) c.max_blocks * kAtabRows * 32 * sizeof(int32_t)));
     CU(cudaMalloc(&ctx->d_chain_errors, sizeof(int)));
     CU(cudaHostAlloc(&ctx->h_chain_errors, sizeof(int), cudaHostAllocDefault));
     const size_t nbu = nbc * ctx->units;
@@ -631,6 +635,7 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFreeHost(ctx->h_bc);
     cudaFree(ctx->d_ck);
     cudaFree(ctx->d_carr_end);
+    cudaFree(ctx->d_atab);
     cudaFree(ctx->d_chain_errors);
     cudaFreeHost(ctx->h_chain_errors);
     cudaFree(ctx->d_guess);
@@ -706,6 +711,7 @@ int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream_, i
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
     SynthArgs a = ctx->last;
     if (dst_device) a.out = dst_device;
+    if (kernel_mask & 8) CU(launch_tables(a, s));
     if (kernel_mask & 4) CU(launch_probe(a, s));
     if (kernel_mask & 1) CU(launch_checkpoints(a, s));
     if (kernel_mask & 2) CU(launch_synth(a, s));

@@ -9,6 +9,9 @@
 //   k_probe       : one thread per (block, channel) walks the carrier NCO through the
 //                   block from a GUESSED start phase (speculative, parallel in time);
 //                   the host turns the probes into exact start phases (nco_exact.h).
+//   k_tables      : one thread per (block, carrier-table row < 256, lane column): the gain-scaled
+//                   carrier table of every block, written once to HBM; k_synth's CTAs (several
+//                   per block) fetch it with one TMA bulk copy each instead of recomputing it.
 //   k_checkpoints : two threads per (block, channel) walk the code and the carrier NCO
 //                   through the block with the exact O(#binade crossings) fast-forward
 //                   and store the state at every run start.
@@ -38,6 +41,35 @@ __device__ __forceinline__ int sine512(int k) {
     const int q = k & 255;
     const int v = c_quarter_sine[q < 128 ? q : 255 - q];
     return k < 256 ? v : -v;
+}
+
+static int group_for(int nchan) { return nchan > 16 ? 32 : (nchan > 8 ? 16 : 8); }
+
+// ---------------------------------------------------------------------------------
+// Carrier tables: atab[block][k][lane] = I + (Q << 16) with I = (int)(cosTable512[k] * gain),
+// Q = (int)(sinTable512[k] * gain) of the lane's channel (gps.c:2781-2782: int product ->
+// double, ONE rounding by the multiply, truncation toward zero). Rows k and k + 256 are
+// negatives of each other (sin[k + 256] = -sin[k], truncation is sign-symmetric), so one
+// thread writes both. Columns repeat with the lane group size (lane = channel + GROUP * j).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tables(SynthArgs a, int group) {
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_blk = 256L * 32;
+    const int b = (int) (idx / per_blk);
+    if (b >= a.nblk) return;
+    const int rem = (int) (idx - (long) b * per_blk), k = rem >> 5, col = rem & 31, c = col % group;
+    const BlockChanDev *bc = a.bc + (size_t) b * a.nchan;
+    int32_t e = 0;
+    if (c < a.nchan && bc[c].prn > 0) {
+        const double gain = bc[c].gain;
+        const int ai = __double2int_rz(__dmul_rn((double) sine512(k + 128), gain));
+        const int aq = __double2int_rz(__dmul_rn((double) sine512(k), gain));
+        e = ai + aq * 65536;
+    }
+    int32_t *t = a.atab + (size_t) b * kAtabRows * 32 + col;
+    t[k * 32] = e;
+    t[(k + 256) * 32] = -e;
+    if (k == 255) t[512 * 32] = -e;                 // guard row 512 = row 511
 }
 
 // ---------------------------------------------------------------------------------
@@ -140,7 +172,6 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
 // ---------------------------------------------------------------------------------
 // Synthesis kernel
 // ---------------------------------------------------------------------------------
-constexpr int kAtabRows = 513;          // row 512 is never addressed (carr_phase < 1.0 always), kept as a guard
 constexpr int kMaxWarps = 24;
 constexpr int kChunkMax = 64;           // samples per chunk (chip window refill / output flush)
 
@@ -149,7 +180,8 @@ struct SynthSmem {
     int32_t atab[kAtabRows][32];                 // [k][lane]: I + (Q << 16), gain-scaled (gps.c:2781-2782)
     uint32_t cabits[kChipWords][GROUP];          // [word][channel]: C/A chips, bit n = ca[n mod 1023], n < 1056
     uint32_t nav[kNavWords][GROUP];              // NAV words of this block's frame
-    alignas(16) int32_t stage[kMaxWarps][kChunkMax * (32 / GROUP)]; // per-warp staging of one chunk of samples per run
+    alignas(16) int32_t stage[kMaxWarps][kChunkMax * (32 / GROUP)];
+    alignas(8) uint64_t bar;                     // mbarrier of the carrier-table bulk copy // per-warp staging of one chunk of samples per run
 };
 
 template <int GROUP>
@@ -177,18 +209,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
     const BlockChanDev *bc = a.bc + (size_t) b * a.nchan;
 
     // ---- per-CTA tables ----------------------------------------------------------
-    for (int i = tid; i < kAtabRows * 32; i += nthr) {
-        const int k = i >> 5, col = i & 31, c = col % GROUP;
-        int32_t e = 0;
-        if (c < a.nchan && bc[c].prn > 0) {
-            const int kk = k < 512 ? k : 511;
-            const double gain = bc[c].gain;
-            // int product -> double, one rounding by the multiply, truncation toward zero
-            const int ai = __double2int_rz(__dmul_rn((double) sine512(kk + 128), gain));
-            const int aq = __double2int_rz(__dmul_rn((double) sine512(kk), gain));
-            e = ai + aq * 65536;
-        }
-        sm.atab[k][col] = e;
+    // carrier table of this block: one TMA bulk copy global -> shared, completion on an mbarrier;
+    // the small tables are gathered by the threads meanwhile
+    const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&sm.bar);
+    constexpr uint32_t kAtabBytes = kAtabRows * 32 * 4;
+    static_assert(kAtabBytes % 16 == 0, "bulk copy size");
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int32_t *src = a.atab + (size_t) b * kAtabRows * 32;
+        const uint32_t dst = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][0]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kAtabBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(kAtabBytes), "r"(bar)
+                     : "memory");
     }
     for (int i = tid; i < kChipWords * GROUP; i += nthr) {
         const int w = i / GROUP, c = i % GROUP;
@@ -202,6 +239,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         if (c < a.nchan && bc[c].prn > 0)
             v = a.nav[((size_t) bc[c].frame * a.nchan + c) * kNavWords + w];
         sm.nav[w][c] = v;
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                         : "=r"(done)
+                         : "r"(bar), "r"(0)
+                         : "memory");
     }
     __syncthreads();
 
@@ -385,8 +430,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
 // ---------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------
-static int group_for(int nchan) { return nchan > 16 ? 32 : (nchan > 8 ? 16 : 8); }
-
 template <int GROUP>
 static cudaError_t launch_synth_t(const SynthArgs &a, cudaStream_t s) {
     const int rpw = 32 / GROUP;
@@ -419,6 +462,12 @@ void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *sme
     *ctas = a.nblk * a.ctas_per_block;
     *threads = ((a.runs_per_cta + rpw - 1) / rpw) * 32;
     *smem = grp == 32 ? sizeof(SynthSmem<32>) : (grp == 16 ? sizeof(SynthSmem<16>) : sizeof(SynthSmem<8>));
+}
+
+cudaError_t launch_tables(const SynthArgs &a, cudaStream_t s) {
+    const long total = (long) a.nblk * 256 * 32;
+    k_tables<<<(unsigned) ((total + 255) / 256), 256, 0, s>>>(a, group_for(a.nchan));
+    return cudaGetLastError();
 }
 
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {

@@ -8,6 +8,7 @@ namespace gpsb200 {
 constexpr int kBlockSamples = 300000;   // sdr.h:26
 constexpr int kNavWords = 60;           // gps.h:52
 constexpr int kChipWords = 33;          // 1023 chips, periodically extended to 33 x 32 bits
+constexpr int kAtabRows = 513;          // carrier table rows; row 512 is never addressed (carr_phase < 1.0 always), a guard
 
 // One record per (block, channel slot), written by the host, read by both kernels.
 struct BlockChanDev {
@@ -45,6 +46,7 @@ struct SynthArgs {
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
+    int32_t *atab;            // [nblk][513][32] gain-scaled carrier table per block: I + (Q << 16), column = lane
     double *carr_end;         // [nblk][nchan] carrier phase after the block
     int *chain_errors;        // self-check counter: blocks whose walked end phase != the next block's start phase
     void *out;                // nblk * 600000 int8 or int16
@@ -52,6 +54,8 @@ struct SynthArgs {
     int units, unit_samples;
 };
 
+// Gain-scaled carrier tables of every block (gps.c:2781-2782), fetched by k_synth with TMA bulk copies.
+cudaError_t launch_tables(const SynthArgs &a, cudaStream_t s);
 // Speculative carrier walk of every (block, channel) from a guessed start phase (nco_exact.h).
 cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s);
 // Run-start checkpoints for every (block, channel): exact walk, O(#binade crossings).
