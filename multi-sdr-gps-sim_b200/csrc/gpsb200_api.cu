@@ -1,5 +1,6 @@
 // C ABI of libgpsb200.so (include/gpsb200.h): context, pipeline, host share of the carrier chain.
 //
+// (k_tables writes the per-block carrier tables k_synth fetches by TMA; it depends on the parameters only.)
 // Host work per block and channel is what the reference's 10 Hz path hands to its sample loop
 // (gps.c:2731-2765) plus ONE thing the loop carries implicitly: the carrier phase at the start
 // of the block, which in the reference is whatever 300000 sequential FP64 additions left behind
