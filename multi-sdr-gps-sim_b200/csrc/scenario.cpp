@@ -15,11 +15,14 @@
 // Scope notes: almanac pages are not generated (the reference run with its almanac
 // disabled, as in all BASELINE configs); downloads, interactive motion and
 // the HackRF/Pluto specifics (except the Pluto gain doubling) are out of scope.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gpsb200.h"
@@ -432,19 +435,21 @@ void build_nav_frame(const GpsTime &g, Channel &ch, bool init) {
 }
 
 // ---- code phase / NAV position at the start of a block (gps.c:2033-2064) -------------------------------------
-void block_start_state(Channel &ch, const Range &rho1, double dt) {
-    const double rhorate = (rho1.range - ch.rho0.range) / dt;
-    ch.f_carr = -rhorate / kLambda;
-    ch.f_code = kCodeFreq + ch.f_carr * kCarrToCode;
-    const double ms = ((gps_diff(ch.rho0.g, ch.g0) + 6.0) - ch.rho0.range / kC) * 1000.0;
+// A pure function of (the range the reference holds in chan.rho0, the NAV frame start chan.g0, this block's
+// range): the form the block-parallel scenario builder needs. Results in `out` (f_carr, f_code, code_phase,
+// iword, ibit, icode).
+void block_start_pure(const Range &rho0, const GpsTime &frame_g0, const Range &rho1, double dt, gpsb200_chan_t &out) {
+    const double rhorate = (rho1.range - rho0.range) / dt;
+    out.f_carr = -rhorate / kLambda;
+    out.f_code = kCodeFreq + out.f_carr * kCarrToCode;
+    const double ms = ((gps_diff(rho0.g, frame_g0) + 6.0) - rho0.range / kC) * 1000.0;
     int ims = (int) ms;
-    ch.code_phase = (ms - (double) ims) * GPSB200_CA_LEN;
-    ch.iword = ims / 600;
-    ims -= ch.iword * 600;
-    ch.ibit = ims / 20;
-    ims -= ch.ibit * 20;
-    ch.icode = ims;
-    ch.rho0 = rho1;
+    out.code_phase = (ms - (double) ims) * GPSB200_CA_LEN;
+    out.iword = ims / 600;
+    ims -= out.iword * 600;
+    out.ibit = ims / 20;
+    ims -= out.ibit * 20;
+    out.icode = ims;
 }
 
 // ---- RINEX v2 navigation reader (gps.c:1131-1505) ----------------------------------------------------------------
@@ -739,6 +744,7 @@ int build(gpsb200_scenario *S) {
     if (ieph < 0) return fail(S, "no current set of ephemerides");
 
     std::vector<Channel> chan(C);
+    std::vector<char> fresh(C, 0);                  // slot (re)allocated since the last epoch snapshot
     int allocated[kMaxSat];
     for (int sv = 0; sv < kMaxSat; sv++) allocated[sv] = -1;
     double ant_pat[37];
@@ -767,6 +773,7 @@ int build(gpsb200_scenario *S) {
                         if (chan[i].prn == 0) {
                             Channel &ch = chan[i];
                             ch.prn = sv + 1;
+                            fresh[i] = 1;
                             // the reference never initialises channel_t.ipage (gps.c:2086 reads it);
                             // its -Og build sees zeroed stack there, which is what is reproduced here
                             build_subframes(set[sv], io, ch.sbf);
@@ -788,48 +795,73 @@ int build(gpsb200_scenario *S) {
         }
     };
 
+    // The reference's loop (gps.c:2731-2930) does two things per 0.1 s block: the per-channel range /
+    // code-phase / gain update, which depends only on this block's and the previous block's range, and,
+    // every 30 s, the NAV frame roll / ephemeris roll / reallocation. Here: (A) one cheap sequential pass
+    // runs the 30 s events and records, per EPOCH (the blocks between two events), which satellite sits in
+    // which slot, with which ephemeris set and NAV frame; (B) all ranges and (C) all block-start states are
+    // then computed block-parallel. Every number comes out of the same function with the same arguments
+    // as in the sequential order, so the result is bit-identical (tests/test_scenario.py).
+    struct Epoch {
+        int b_first = 0, ieph = 0;
+        std::vector<int> prn;
+        std::vector<char> fresh;
+        std::vector<GpsTime> frame_g0;
+        std::vector<Range> rho_alloc;
+        std::vector<double> carr_phase;
+    };
+    std::vector<Epoch> epochs;
+    auto snapshot = [&](int b_first, int ieph_now) {
+        Epoch e;
+        e.b_first = b_first;
+        e.ieph = ieph_now;
+        e.prn.resize(C);
+        e.fresh = fresh;
+        e.frame_g0.resize(C);
+        e.rho_alloc.resize(C);
+        e.carr_phase.resize(C);
+        for (int i = 0; i < C; i++) {
+            e.prn[i] = chan[i].prn;
+            e.frame_g0[i] = chan[i].g0;
+            e.rho_alloc[i] = chan[i].rho0;           // only read where fresh[i]
+            e.carr_phase[i] = chan[i].carr_phase;
+        }
+        std::fill(fresh.begin(), fresh.end(), 0);
+        epochs.push_back(std::move(e));
+    };
+
     GpsTime grx = gps_add(g0, 0.0);
     allocate(eph[ieph], grx);
     grx = gps_add(grx, 0.1);
 
     S->nblocks = numd - 1;
-    S->chans.assign((size_t) S->nblocks * C, gpsb200_chan_t{});
+    const int NB = S->nblocks;
+    S->chans.assign((size_t) NB * C, gpsb200_chan_t{});
     S->nav.clear();
     S->nframes = 0;
+    std::vector<GpsTime> grx_of(NB);
+    std::vector<int> epoch_of(NB), frame_of(NB);
     std::vector<uint32_t> cur((size_t) C * GPSB200_NAV_WORDS, 0), last;
+    // ---- (A) sequential: times, 30 s events, NAV frame table ------------------------------------------------
+    snapshot(0, ieph);
+    bool words_may_have_changed = true;
     for (int iumd = 1; iumd < numd; iumd++) {
         const int b = iumd - 1;
+        grx_of[b] = grx;
+        epoch_of[b] = (int) epochs.size() - 1;
         // NAV frame table: a new frame whenever any channel's words changed (every 30 s / reallocation)
-        for (int i = 0; i < C; i++)
-            for (int k = 0; k < GPSB200_NAV_WORDS; k++)
-                cur[(size_t) i * GPSB200_NAV_WORDS + k] = chan[i].prn > 0 ? chan[i].dwrd[k] : 0u;
-        if (cur != last) {
-            S->nav.insert(S->nav.end(), cur.begin(), cur.end());
-            S->nframes++;
-            last = cur;
+        if (words_may_have_changed) {
+            for (int i = 0; i < C; i++)
+                for (int k = 0; k < GPSB200_NAV_WORDS; k++)
+                    cur[(size_t) i * GPSB200_NAV_WORDS + k] = chan[i].prn > 0 ? chan[i].dwrd[k] : 0u;
+            if (cur != last) {
+                S->nav.insert(S->nav.end(), cur.begin(), cur.end());
+                S->nframes++;
+                last = cur;
+            }
+            words_may_have_changed = false;
         }
-        for (int i = 0; i < C; i++) {
-            gpsb200_chan_t &o = S->chans[(size_t) b * C + i];
-            o.nav_frame = S->nframes - 1;
-            Channel &ch = chan[i];
-            if (ch.prn <= 0) continue;
-            const Eph &e = eph[ieph][ch.prn - 1];
-            const Range rho = pseudo_range(e, io, grx, pos_at(iumd));          // gps.c:2738
-            block_start_state(ch, rho, 0.1);                                   // gps.c:2744
-            const double path_loss = 20200000.0 / rho.d;                       // gps.c:2749
-            const int ibs = (int) ((90.0 - rho.el * kR2D) / 5.0);
-            double gain = (double) (path_loss * ant_pat[ibs]);
-            if (cfg.pluto_gain) gain *= 2;                                     // gps.c:2759-2763
-            o.prn = ch.prn;
-            o.iword = ch.iword;
-            o.ibit = ch.ibit;
-            o.icode = ch.icode;
-            o.f_carr = ch.f_carr;
-            o.f_code = ch.f_code;
-            o.carr_phase = ch.carr_phase;           // meaningful for a slot's first block only
-            o.code_phase = ch.code_phase;
-            o.gain = gain;
-        }
+        frame_of[b] = S->nframes - 1;
         // every 30 s: NAV frame roll, ephemeris set roll, reallocation (gps.c:2870-2930)
         const int igrx = (int) (grx.sec * 10.0 + 0.5);
         if (igrx % 300 == 0) {
@@ -846,9 +878,60 @@ int build(gpsb200_scenario *S) {
                         break;
                     }
             allocate(eph[ieph], grx);
+            if (iumd + 1 < numd) snapshot(b + 1, ieph);
+            words_may_have_changed = true;
         }
         grx = gps_add(grx, 0.1);
     }
+
+    // ---- (B) + (C) block-parallel ----------------------------------------------------------------------------
+    const Eph(*E)[kMaxSat] = eph;                   // `eph` is thread_local: hand the workers THIS thread's table
+    std::vector<Range> rho((size_t) NB * C);
+    int nthr = (int) std::thread::hardware_concurrency();
+    if (const char *ev = getenv("GPSB200_SCENARIO_THREADS")) nthr = atoi(ev);
+    nthr = std::max(1, std::min(std::min(nthr, 16), NB / 64 + 1));
+    auto parallel_blocks = [&](const std::function<void(int, int)> &job) {
+        if (nthr == 1) {
+            job(0, NB);
+            return;
+        }
+        std::vector<std::thread> th;
+        const int per = (NB + nthr - 1) / nthr;
+        for (int t = 0; t < nthr; t++) {
+            const int lo = t * per, hi = std::min(NB, lo + per);
+            if (lo < hi) th.emplace_back(job, lo, hi);
+        }
+        for (auto &t : th) t.join();
+    };
+    parallel_blocks([&](int lo, int hi) {            // (B) this block's pseudorange per channel (gps.c:2738)
+        for (int b = lo; b < hi; b++) {
+            const Epoch &ep = epochs[epoch_of[b]];
+            for (int i = 0; i < C; i++)
+                if (ep.prn[i] > 0) rho[(size_t) b * C + i] = pseudo_range(E[ep.ieph][ep.prn[i] - 1], io, grx_of[b], pos_at(b + 1));
+        }
+    });
+    parallel_blocks([&](int lo, int hi) {            // (C) block-start state and gain (gps.c:2744-2763)
+        for (int b = lo; b < hi; b++) {
+            const Epoch &ep = epochs[epoch_of[b]];
+            for (int i = 0; i < C; i++) {
+                gpsb200_chan_t &o = S->chans[(size_t) b * C + i];
+                o.nav_frame = frame_of[b];
+                if (ep.prn[i] <= 0) continue;
+                const Range &r1 = rho[(size_t) b * C + i];
+                // the range the reference still holds in chan[i].rho0: the allocation's for a slot's first
+                // block, else the previous block's (possibly computed with the previous ephemeris set)
+                const Range &r0 = (b == ep.b_first && ep.fresh[i]) ? ep.rho_alloc[i] : rho[(size_t) (b - 1) * C + i];
+                block_start_pure(r0, ep.frame_g0[i], r1, 0.1, o);
+                const double path_loss = 20200000.0 / r1.d;                     // gps.c:2749
+                const int ibs = (int) ((90.0 - r1.el * kR2D) / 5.0);
+                double gain = (double) (path_loss * ant_pat[ibs]);
+                if (cfg.pluto_gain) gain *= 2;                                  // gps.c:2759-2763
+                o.prn = ep.prn[i];
+                o.carr_phase = ep.carr_phase[i];   // meaningful for a slot's first block only
+                o.gain = gain;
+            }
+        }
+    });
     return GPSB200_OK;
 }
 

@@ -42,7 +42,12 @@ SCENARIOS = {
     "sky12_track_60s_i16": (12, "ref_dump12", 60, ["--iq16", "-m", "@MOTION"], []),
     # the same constellation written as RINEX 3 and read by the reference's readRinex3 (-3)
     "sky12_rinex3_3s_i8": (12, "ref_dump12", 3, ["-3"], []),
+    # a satellite rises into a free slot at 240 s and another sets at 300 s (allocateChannel, gps.c:2142-2235):
+    # 60N 140E, 32 channels, 310 s. Parameters kept only around the events; digests of every block.
+    "sky32_lat60_310s_i8": (32, "ref_dump32", 310, [], []),
 }
+LOCS = {"sky32_lat60_310s_i8": "60.0,140.0,0.0"}
+CHAN_KEEP = {"sky32_lat60_310s_i8": list(range(0, 3)) + list(range(2396, 2405)) + list(range(2996, 3005)) + [3098]}
 
 
 def run(name):
@@ -56,7 +61,7 @@ def run(name):
             mot = os.path.join(td, "track.csv")
             write_motion(mot, int(secs * 10))
             extra = [mot if x == "@MOTION" else x for x in extra]
-        subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOC, "-d", str(secs),
+        subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOCS.get(name, LOC), "-d", str(secs),
                                "-s", START, "--iq", iq, "--params", par] + extra,
                               stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
         p = refdump.read_params(par)
@@ -72,6 +77,12 @@ def run(name):
             nav_all = refdump.nav_table(p)[:2]
         else:
             ch_keep, nav_all = ch, refdump.nav_table(p)
+        extra_out = {}
+        if name in CHAN_KEEP:
+            idx_keep = np.array(CHAN_KEEP[name], np.int32)
+            ch_keep = ch[idx_keep]
+            extra_out["chans_idx"] = idx_keep
+            extra_out["prn_of_block"] = ch["prn"].astype(np.int8)      # slot occupancy of every block
         out = dict(
             max_chan=np.int32(p["max_chan"]), sample_size=np.int32(p["sample_size"]),
             chans=ch_keep, nav_words=nav_all, crcs=crcs,
@@ -90,6 +101,7 @@ def run(name):
             idx[b] = len(frames) - 1
         out["nav_frames"] = np.stack(frames)
         out["nav_frame_of_block"] = idx
+        out.update(extra_out)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "blocks", nblk, "chan", p["max_chan"], "frames", len(frames),
               "active", int((ch["prn"][0] > 0).sum()))

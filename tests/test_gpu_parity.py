@@ -207,6 +207,19 @@ def test_config1_from_rinex_file_to_reference_stream(name, nsat, chan, secs, tmp
     assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
 
 
+def test_reallocation_310s_from_rinex_file_to_reference_stream(tmp_path):
+    """60N 140E, 32 channels, 310 s: a satellite rises into a free slot at 240 s (fresh carrier phase, NAV frame
+    built for the new slot) and another sets at 300 s. RINEX in, all 3099 blocks equal to the reference's stream."""
+    g = scenario.load_golden("sky32_lat60_310s_i8")
+    ch, nav = gps.scenario(_nav_file(tmp_path, 32), 60.0, 140.0, 0.0, seconds=310, max_chan=32, start=(2024, 1, 7, 2, 0, 0.0))
+    assert ch.shape[0] == 3099
+    with gps.Context(32, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 1)
+    bad = np.nonzero(scenario.crc_blocks(out) != g["crcs"][:, 0])[0]
+    assert bad.size == 0, bad[:10]
+
+
 def test_cli_writes_reference_iqfile_and_stock_compat_file(tmp_path):
     import os
     import subprocess

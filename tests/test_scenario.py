@@ -65,6 +65,45 @@ def test_scenario_engine_matches_reference_dump_bit_for_bit(name, tmp_path):
         assert np.array_equal(nav[fidx[b]][a], frames[fidx[b]][a])
 
 
+LOC60 = (60.0, 140.0, 0.0)
+
+
+def test_reallocation_310s_matches_reference_dump_and_is_thread_invariant(tmp_path, monkeypatch):
+    """A satellite rises into a free slot at 240 s, another one sets at 300 s (allocateChannel every 30 s,
+    gps.c:2142-2235, 2909): slot occupancy of all 3099 blocks, every parameter around the events and every
+    NAV frame against the reference's dump; and the block-parallel builder gives the same bytes for 1 and
+    16 threads."""
+    g = scenario.load_golden("sky32_lat60_310s_i8")
+    nav_file = make_nav(tmp_path, 32)
+    runs = []
+    for thr in ("1", "16"):
+        monkeypatch.setenv("GPSB200_SCENARIO_THREADS", thr)
+        runs.append(gps.scenario(nav_file, *LOC60, seconds=310, max_chan=32, start=START))
+    (got, nav), (got16, nav16) = runs
+    assert got.tobytes() == got16.tobytes() and nav.tobytes() == nav16.tobytes()
+    prn = g["prn_of_block"].astype(np.int32)
+    assert got.shape == prn.shape and np.array_equal(got["prn"], prn)
+    changes = np.nonzero((prn[1:] != prn[:-1]).any(axis=1))[0] + 1
+    assert list(changes) == [2400, 3000]                     # the fixture really contains both events
+    idx, want = g["chans_idx"], g["chans"]
+    for k, b in enumerate(idx):
+        act = want["prn"][k] > 0
+        for f in ("iword", "ibit", "icode"):
+            assert np.array_equal(got[f][b][act], want[f][k][act]), (f, b)
+        for f in ("f_carr", "f_code", "code_phase", "gain"):
+            assert np.array_equal(got[f][b][act].view(np.uint64), want[f][k][act].view(np.uint64)), (f, b)
+    # the slot filled at block 2400 starts from the allocation-time carrier phase (gps.c:2203-2210)
+    k = list(idx).index(2400)
+    new = (prn[2400] > 0) & (prn[2399] == 0)
+    assert new.sum() == 1
+    assert np.array_equal(got["carr_phase"][2400][new].view(np.uint64), want["carr_phase"][k][new].view(np.uint64))
+    frames, fidx = g["nav_frames"], g["nav_frame_of_block"]
+    assert len(nav) == len(frames) and np.array_equal(got["nav_frame"][:, 0], fidx)
+    for b in (0, 2399, 2400, 2999, 3000, 3098):
+        a = prn[b] > 0
+        assert np.array_equal(nav[fidx[b]][a], frames[fidx[b]][a]), b
+
+
 def test_scenario_errors():
     with pytest.raises(gps.GpsB200Error):
         gps.scenario("/nonexistent.nav", *LOC, seconds=5)
