@@ -86,6 +86,9 @@ typedef struct gpsb200_stats {
     int32_t chain_fallbacks;   /* blocks whose speculative carrier probe was rejected (exact sequential walk used) */
 } gpsb200_stats_t;
 
+/* Threading: a context may be used by one thread at a time; different contexts (same or different devices)
+ * may be used concurrently from different threads, every entry point selects the context's device itself.
+ * The FIFO below is process-global with one producer and one consumer, as in the reference (fifo.c:21-29). */
 int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out);
 void gpsb200_destroy(gpsb200_ctx_t *ctx);
 const char *gpsb200_last_error(const gpsb200_ctx_t *ctx);

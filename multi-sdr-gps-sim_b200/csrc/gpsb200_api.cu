@@ -322,6 +322,7 @@ int check_call(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int ncha
         (sample_size != GPSB200_SC08 && sample_size != GPSB200_SC16))
         return fail(ctx, GPSB200_ERR_ARG, "bad arguments (nchan must equal cfg.max_chan; 1 <= nblk <= cfg.max_blocks)");
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
+    CU(cudaSetDevice(ctx->cfg.device));     // the caller may be a thread that never selected the context's device
     return GPSB200_OK;
 }
 
@@ -629,6 +630,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
 
 void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     if (!ctx) return;
+    if (ctx->s_compute) cudaSetDevice(ctx->cfg.device);
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     if (ctx->s_pre) cudaStreamSynchronize(ctx->s_pre);
@@ -680,6 +682,7 @@ int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans
                                  const double *phase_in, double *phase_out) {
     if (!ctx || !chans || !phase_out || nblk < 0 || nchan != ctx->cfg.max_chan) return GPSB200_ERR_ARG;
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
+    CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t s = ctx->s_compute;
     std::vector<ChainState> chain(nchan);
     if (phase_in && nblk > 0)
@@ -709,6 +712,7 @@ int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans
 
 int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream_, int kernel_mask) {
     if (!ctx || !ctx->have_last) return GPSB200_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
     SynthArgs a = ctx->last;
     if (dst_device) a.out = dst_device;

@@ -281,6 +281,32 @@ def test_channel_reallocation_and_gaps_vs_oracle():
         assert np.array_equal(cp, carr)
 
 
+def test_two_contexts_used_concurrently_from_two_threads():
+    import threading
+    cases = [gps.synthetic_chans(40, 32, seed=901), gps.synthetic_chans(40, 12, seed=902)]
+    want = []
+    for ch, nav in cases:
+        with gps.Context(ch.shape[1], 40) as ctx:
+            ctx.set_nav_frames(nav)
+            want.append(ctx.synth_blocks(ch, 1)[0])
+    got = [None, None]
+
+    def work(k):
+        ch, nav = cases[k]
+        with gps.Context(ch.shape[1], 40) as ctx:
+            ctx.set_nav_frames(nav)
+            for _ in range(3):
+                got[k] = ctx.synth_blocks(ch, 1)[0]
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(2):
+        assert np.array_equal(got[k], want[k]), k
+
+
 def test_single_block_call_latency_is_far_below_real_time():
     # the reference's cadence: one 0.1 s block per call
     import time
