@@ -281,6 +281,20 @@ def test_channel_reallocation_and_gaps_vs_oracle():
         assert np.array_equal(cp, carr)
 
 
+@pytest.mark.parametrize("knob,val", [("GPSB200_UNITS", "5"), ("GPSB200_GRADED_CHUNKS", "0")])
+def test_experiment_knobs_do_not_change_the_output(knob, val, monkeypatch):
+    # the knobs of README.md only move work around (carrier-chain units per block, download chunking)
+    ch, nav = gps.synthetic_chans(300, 32, seed=4242)
+    with gps.Context(32, 300) as ctx:
+        ctx.set_nav_frames(nav)
+        want, cp = ctx.synth_blocks(ch, 1)
+    monkeypatch.setenv(knob, val)
+    with gps.Context(32, 300) as ctx:
+        ctx.set_nav_frames(nav)
+        got, cp2 = ctx.synth_blocks(ch, 1)
+    assert np.array_equal(got, want) and np.array_equal(cp, cp2)
+
+
 def test_two_contexts_used_concurrently_from_two_threads():
     import threading
     cases = [gps.synthetic_chans(40, 32, seed=901), gps.synthetic_chans(40, 12, seed=902)]
