@@ -391,10 +391,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),
                          # ncu --set full (profiles/r1_ncu_metrics.csv): dram read+write of one 600-block int8
-                         # launch = 98.4 + 304.4 MB for 360 MB of algorithmic bytes; scaled to this launch
-                         "traffic": (int(alg_bytes * (98.4 + 304.4) / 360.0) if not args.iq16 else None),
+                         # launch = 98.7 + 304.7 MB for 360 MB of algorithmic bytes; scaled to this launch
+                         "traffic": (int(alg_bytes * (98.7 + 304.7) / 360.0) if not args.iq16 else None),
                          "peak_source": peak_src,
-                         "note": "path is issue-slot / shared-memory bound (~14.1 SASS instructions per 32-channel "
+                         "note": "path is issue-slot / shared-memory bound (~13.9 SASS instructions per 32-channel "
                                  "sample step), not HBM bound; see DESIGN.md and profiles/"},
             "e2e": {"value": round(e2e_value, 1), "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(stats.h2d_bytes) * 1, "d2h_bytes_per_step": int(stats.d2h_bytes),
