@@ -158,7 +158,20 @@ def write3(path, nsat):
         f.write("\n".join(L) + "\n")
 
 
-def write(path, nsat):
+def propagate(el, prn, hours):
+    """The same orbit re-expressed at toe + hours (continuous with the first set): M0 and OMEGA0 advance
+    with their rates (satpos, reference gps.c:361-460)."""
+    if hours == 0:
+        return dict(el), 1e-5 * prn
+    dt = 3600.0 * hours
+    n = math.sqrt(GM / (el["sqrta"] ** 2) ** 3) + 4.5e-9
+    e2 = dict(el)
+    e2["m0"] = (el["m0"] + n * dt + math.pi) % (2 * math.pi) - math.pi
+    e2["omg0"] = (el["omg0"] + (-8e-9) * dt + math.pi) % (2 * math.pi) - math.pi
+    return e2, 1e-5 * prn + 1e-12 * prn * dt
+
+
+def write(path, nsat, sets=1):
     L = []
 
     def hdr(body, label):
@@ -171,20 +184,24 @@ def write(path, nsat):
     hdr("   " + d19(9.313225746155e-10) + d19(8.881784197001e-16) + "%9d%9d" % (61440, WEEK), "DELTA-UTC: A0,A1,T,W")
     hdr("%6d" % 18, "LEAP SECONDS")
     hdr("", "END OF HEADER")
-    for prn, (lat, lon) in zip(range(1, nsat + 1), sub_points(nsat)):
-        el = elements(prn, lat, lon)
-        L.append("%2d 24  1  7  2  0  0.0" % prn + d19(1e-5 * prn) + d19(1e-12 * prn) + d19(0.0))
-        rows = [
-            (float(prn), 10.0 + prn, 4.5e-9, el["m0"]),                     # IODE Crs dn M0
-            (1e-6, el["ecc"], 5e-6, el["sqrta"]),                           # Cuc e Cus sqrtA
-            (TOE_SOW, 1e-8 * prn, el["omg0"], -1e-8 * prn),                 # toe Cic OMEGA0 Cis
-            (el["inc"], 200.0 + prn, el["aop"], -8e-9),                     # i0 Crc omega OMEGADOT
-            (1e-10, 1.0, float(WEEK), 0.0),                                 # IDOT codesL2 week L2P
-            (0.0, 0.0, -1e-8, float(prn)),                                  # sva svh tgd iodc
-            (TOE_SOW - 30.0, 4.0, 0.0, 0.0),                                # tx time, fit
-        ]
-        for r in rows:
-            L.append("   " + "".join(d19(v) for v in r))
+    # one record set every two hours (the reference starts a new set when toc advances by more than an hour,
+    # gps.c:1380-1392, and rolls to it one hour before its toc, gps.c:2890-2905)
+    for k in range(sets):
+        for prn, (lat, lon) in zip(range(1, nsat + 1), sub_points(nsat)):
+            el, af0 = propagate(elements(prn, lat, lon), prn, 2 * k)
+            toe = TOE_SOW + 7200.0 * k
+            L.append("%2d 24  1  7 %2d  0  0.0" % (prn, 2 + 2 * k) + d19(af0) + d19(1e-12 * prn) + d19(0.0))
+            rows = [
+                (float(prn + 40 * k), 10.0 + prn, 4.5e-9, el["m0"]),            # IODE Crs dn M0
+                (1e-6, el["ecc"], 5e-6, el["sqrta"]),                           # Cuc e Cus sqrtA
+                (toe, 1e-8 * prn, el["omg0"], -1e-8 * prn),                     # toe Cic OMEGA0 Cis
+                (el["inc"], 200.0 + prn, el["aop"], -8e-9),                     # i0 Crc omega OMEGADOT
+                (1e-10, 1.0, float(WEEK), 0.0),                                 # IDOT codesL2 week L2P
+                (0.0, 0.0, -1e-8, float(prn + 40 * k)),                         # sva svh tgd iodc
+                (toe - 30.0, 4.0, 0.0, 0.0),                                    # tx time, fit
+            ]
+            for r in rows:
+                L.append("   " + "".join(d19(v) for v in r))
     with open(path, "w") as f:
         f.write("\n".join(L) + "\n")
 
@@ -194,5 +211,9 @@ if __name__ == "__main__":
     ap.add_argument("--nsat", type=int, default=12)
     ap.add_argument("--out", required=True)
     ap.add_argument("--v3", action="store_true", help="write RINEX 3 instead of RINEX 2")
+    ap.add_argument("--sets", type=int, default=1, help="ephemeris sets, two hours apart (RINEX 2 only)")
     a = ap.parse_args()
-    (write3 if a.v3 else write)(a.out, a.nsat)
+    if a.v3:
+        write3(a.out, a.nsat)
+    else:
+        write(a.out, a.nsat, a.sets)

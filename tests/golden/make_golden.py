@@ -46,8 +46,14 @@ SCENARIOS = {
     # 60N 140E, 32 channels, 310 s. Parameters kept only around the events; digests of every block.
     "sky32_lat60_310s_i8": (32, "ref_dump32", 310, [], []),
 }
+    # two ephemeris sets (02:00 and 04:00), start 02:55:00: the reference rolls to the second set at the first
+    # 30 s boundary after 03:00:00 (gps.c:2890-2905) and rebuilds every channel's subframes. 400 s, 12 channels.
+SCENARIOS["sky12_ephroll_400s_i8"] = (12, "ref_dump12", 400, [], [])
 LOCS = {"sky32_lat60_310s_i8": "60.0,140.0,0.0"}
-CHAN_KEEP = {"sky32_lat60_310s_i8": list(range(0, 3)) + list(range(2396, 2405)) + list(range(2996, 3005)) + [3098]}
+STARTS = {"sky12_ephroll_400s_i8": "2024/01/07,02:55:00"}
+RINEX_ARGS = {"sky12_ephroll_400s_i8": ["--sets", "2"]}
+CHAN_KEEP = {"sky32_lat60_310s_i8": list(range(0, 3)) + list(range(2396, 2405)) + list(range(2996, 3005)) + [3098],
+             "sky12_ephroll_400s_i8": list(range(0, 3)) + list(range(3290, 3312)) + [3998]}
 
 
 def run(name):
@@ -55,14 +61,15 @@ def run(name):
     with tempfile.TemporaryDirectory() as td:
         nav = os.path.join(td, "sky.nav")
         subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "gen_rinex.py"),
-                               "--nsat", str(nsat), "--out", nav] + (["--v3"] if "-3" in extra else []))
+                               "--nsat", str(nsat), "--out", nav] + (["--v3"] if "-3" in extra else []) +
+                              RINEX_ARGS.get(name, []))
         iq, par = os.path.join(td, "iq.bin"), os.path.join(td, "p.bin")
         if "@MOTION" in extra:
             mot = os.path.join(td, "track.csv")
             write_motion(mot, int(secs * 10))
             extra = [mot if x == "@MOTION" else x for x in extra]
         subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOCS.get(name, LOC), "-d", str(secs),
-                               "-s", START, "--iq", iq, "--params", par] + extra,
+                               "-s", STARTS.get(name, START), "--iq", iq, "--params", par] + extra,
                               stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
         p = refdump.read_params(par)
         dt = np.int16 if p["sample_size"] == 2 else np.int8

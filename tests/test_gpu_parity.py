@@ -220,6 +220,25 @@ def test_reallocation_310s_from_rinex_file_to_reference_stream(tmp_path):
     assert bad.size == 0, bad[:10]
 
 
+def test_ephemeris_roll_400s_from_rinex_file_to_reference_stream(tmp_path):
+    """Two ephemeris sets in the RINEX file, start 02:55:00, 400 s: the set roll at block 3300 (new subframes, a range
+    step between the sets). RINEX in, all 3999 blocks equal to the reference's stream."""
+    import os
+    import subprocess
+    import sys
+    g = scenario.load_golden("sky12_ephroll_400s_i8")
+    nav_file = tmp_path / "sky12x2.nav"
+    subprocess.check_call([sys.executable, os.path.join(scenario.ROOT, "oracle", "gen_rinex.py"), "--nsat", "12", "--sets", "2",
+                           "--out", str(nav_file)])
+    ch, nav = gps.scenario(str(nav_file), 35.681298, 139.766247, 10.0, seconds=400, max_chan=12, start=(2024, 1, 7, 2, 55, 0.0))
+    assert ch.shape[0] == 3999
+    with gps.Context(12, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 1)
+    bad = np.nonzero(scenario.crc_blocks(out) != g["crcs"][:, 0])[0]
+    assert bad.size == 0, bad[:10]
+
+
 def test_cli_writes_reference_iqfile_and_stock_compat_file(tmp_path):
     import os
     import subprocess

@@ -21,10 +21,11 @@ CASES = {
 }
 
 
-def make_nav(tmp_path, nsat, v3=False):
+def make_nav(tmp_path, nsat, v3=False, sets=1):
     nav = tmp_path / ("sky%d.nav" % nsat)
     subprocess.check_call([sys.executable, os.path.join(scenario.ROOT, "oracle", "gen_rinex.py"),
-                           "--nsat", str(nsat), "--out", str(nav)] + (["--v3"] if v3 else []))
+                           "--nsat", str(nsat), "--out", str(nav)] + (["--v3"] if v3 else []) +
+                          (["--sets", str(sets)] if sets > 1 else []))
     return str(nav)
 
 
@@ -102,6 +103,29 @@ def test_reallocation_310s_matches_reference_dump_and_is_thread_invariant(tmp_pa
     for b in (0, 2399, 2400, 2999, 3000, 3098):
         a = prn[b] > 0
         assert np.array_equal(nav[fidx[b]][a], frames[fidx[b]][a]), b
+
+
+def test_ephemeris_set_roll_400s_matches_reference_dump(tmp_path):
+    """Two ephemeris sets (02:00, 04:00), start 02:55:00: the reference switches to the second set at the
+    first 30 s boundary after 03:00:00 (block 3300, gps.c:2890-2905) and rebuilds all subframes. Slot occupancy
+    of all 3999 blocks, every parameter around the roll and all 14 NAV frames against the reference's dump."""
+    g = scenario.load_golden("sky12_ephroll_400s_i8")
+    got, nav = gps.scenario(make_nav(tmp_path, 12, sets=2), *LOC, seconds=400, max_chan=12, start=(2024, 1, 7, 2, 55, 0.0))
+    assert np.array_equal(got["prn"], g["prn_of_block"])
+    idx, want = g["chans_idx"], g["chans"]
+    assert 3300 in idx and 3301 in idx
+    for k, b in enumerate(idx):
+        act = want["prn"][k] > 0
+        for f in ("iword", "ibit", "icode"):
+            assert np.array_equal(got[f][b][act], want[f][k][act]), (f, b)
+        for f in ("f_carr", "f_code", "code_phase", "gain"):
+            assert np.array_equal(got[f][b][act].view(np.uint64), want[f][k][act].view(np.uint64)), (f, b)
+    frames, fidx = g["nav_frames"], g["nav_frame_of_block"]
+    assert len(nav) == len(frames) == 14 and np.array_equal(got["nav_frame"][:, 0], fidx)
+    assert np.array_equal(nav, frames)
+    # the frame after the roll really carries new ephemeris words (subframes 1-3), not just a new TOW
+    changed = [(frames[i][0] != frames[i - 1][0]).sum() for i in range(1, len(frames))]
+    assert max(changed) > 20 and changed.index(max(changed)) + 1 == 12
 
 
 def test_scenario_errors():
