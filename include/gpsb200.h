@@ -79,7 +79,7 @@ typedef struct gpsb200_ctx gpsb200_ctx_t;
 /* Per-call statistics (filled when the pointer is not NULL). Times in milliseconds. */
 typedef struct gpsb200_stats {
     double host_chain_ms;      /* host share of the carrier chain: start-phase guesses + fix-up scan */
-    double h2d_ms, kernel_ms, d2h_ms;   /* CUDA-event times on the call's stream */
+    double h2d_ms, kernel_ms, d2h_ms;   /* kernel_ms: CUDA-event span of the call's stream; h2d_ms/d2h_ms reserved (0) */
     double checkpoint_kernel_ms, synth_kernel_ms, probe_kernel_ms;
     int64_t h2d_bytes, d2h_bytes;
     int32_t launches;          /* kernels launched by this call */
@@ -121,7 +121,8 @@ int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nb
 /* Same, but the output stays in device memory (dst_device: device pointer with room for
  * nblk * 600000 elements) and the synthesis is only ENQUEUED on `stream` (a cudaStream_t,
  * 0 = the context's own stream) -- the caller synchronizes before reading dst_device. (The
- * call itself waits once for the small carrier-probe round trip.) Used for kernel-only
+ * call itself waits for the small carrier-probe round trip and, with the synthesis already enqueued,
+ * for the device self-check of the carrier chain: a failed check returns GPSB200_ERR_INTERNAL.) Used for kernel-only
  * timing and for multi-GPU time-slice sharding where each rank fills a device buffer. */
 int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                                 int sample_size, void *dst_device, void *stream,
