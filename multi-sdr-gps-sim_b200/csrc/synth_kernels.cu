@@ -279,11 +279,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         return (w >> (29 - ib)) & 1;                          // gps.c:2812
     };
     int dbit = nav_bit(iword, ibit);
-    // Conservative 8-step look-ahead (see below): 8 steps move a phase by at most 8*(|c| + ulp/2),
-    // which 9*|c| + 2^-50 (carrier, phase < 1) resp. 9*d (code, d ~ 0.34 >> ulp) always covers.
-    // "phase + that can leave the range" is tested on the high words only (monotone for positive
-    // doubles, so the test can only err towards "at risk").
-    const double cc9 = 9.0 * fabs(cc) + 0x1p-50, dd9 = 9.0 * dd;
+    // Conservative 8-step look-ahead (see below): 8 steps move a phase by at most 8*(|c| + ulp/2):
+    // carrier (phase < 1, ulp <= 2^-53): 8*|c| + 2^-51, covered by 8*|c| + 2^-50; code (phase < 1024,
+    // ulp <= 2^-43): 8*d + 2^-41, covered by 8*d + 2^-40. "phase + that can leave the range" is tested on
+    // the high words only (monotone for positive doubles), which can only err towards "at risk" -- by up
+    // to 2^-20 relative, far more than any rounding of the thresholds themselves.
+    const double cc9 = 8.0 * fabs(cc) + 0x1p-50, dd9 = 8.0 * dd + 0x1p-40;
     int thr_x_hi = 0x7FFFFFFF, thr_x_lo = -1;                  // cc == 0: never at risk
     if (cc > 0.0) thr_x_hi = cc9 < 1.0 ? __double2hiint(1.0 - cc9) : 0;
     if (cc < 0.0) thr_x_lo = __double2hiint(cc9);
