@@ -106,3 +106,19 @@ def test_oracle_nav_frame_roll_at_30s():
         chans = oracle_lib.make_chans(ch[b], frames[fidx[b]])
         out = oracle_lib.quantize8(oracle_lib.synth_block(chans))
         assert zlib.crc32(out.tobytes()) == crcs[b, 0], b
+
+
+@pytest.mark.parametrize("name,blocks", [("sky32_lat60_310s_i8", (2399, 2400, 2401, 2999, 3000, 3001)),
+                                         ("sky12_ephroll_400s_i8", (3299, 3300, 3301, 3302))])
+def test_oracle_blocks_around_reallocation_and_ephemeris_roll(name, blocks):
+    """The blocks around a slot (re)allocation (a fresh channel's first block, a vacated slot) and around the
+    hourly ephemeris-set roll, each synthesized from the reference's dumped block-start state, against the
+    reference's stream digests."""
+    g = load(name)
+    idx = list(g["chans_idx"])
+    frames, fidx, crcs = g["nav_frames"], g["nav_frame_of_block"], g["crcs"]
+    for b in blocks:
+        row = g["chans"][idx.index(b)]
+        chans = oracle_lib.make_chans(row, frames[fidx[b]])
+        out = oracle_lib.quantize8(oracle_lib.synth_block(chans))
+        assert zlib.crc32(out.tobytes()) == crcs[b, 0], (name, b)
