@@ -40,6 +40,12 @@ BLOCKS_300S = 2999            # -d 300 -> round(10*300) - 1 blocks (gps.c:2703)
 SAMPLES_PER_BLOCK = 300000
 
 
+def note(msg):
+    """Progress line on stderr, flushed: if the box is lost mid-run the record still shows how far we got."""
+    sys.stderr.write("[bench %s rank %s] %s\n" % (time.strftime("%H:%M:%S"), os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -198,16 +204,22 @@ def reference_arm(args):
     if rank != 0:
         return 0
     nchan = args.chan
-    procs = host_cpus()
-    secs = 5.0 if nchan > 12 else 10.0       # 49 / 99 blocks per process and step: a few seconds of CPU
+    procs = min(host_cpus(), 32)              # one copy per usable host core, never more than 32
+    secs = 3.0 if nchan > 12 else 6.0         # 29 / 59 blocks per copy and step: ~2 s of CPU per step
     vals = []
-    for i in range(args.warmup + args.steps):
+    t_arm0 = time.time()
+    warm = min(args.warmup, 2)                # CPU code has nothing to warm beyond the page cache
+    for i in range(warm + args.steps):
+        note("reference arm: step %d/%d, %d copies x %.0f s of signal" % (i + 1, warm + args.steps, procs, secs))
         r = run_reference_cpu(nchan, secs, procs)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_run* not built"}))
             return 0
-        if i >= args.warmup:
+        if i >= warm:
             vals.append(r)
+        if time.time() - t_arm0 > 150.0 and len(vals) >= 2:     # bounded: the whole arm ends within a few minutes
+            note("reference arm: time budget reached after %d timed steps" % len(vals))
+            break
     agg = statistics.mean(v[0] for v in vals)
     single = statistics.mean(statistics.mean(v[1]) for v in vals)
     nblk = int(round(secs * 10)) - 1
@@ -216,7 +228,7 @@ def reference_arm(args):
               "thread (%.2f Msps per copy)") % (procs, nblk, secs, 32 if nchan > 12 else 12, single)
     line = {
         "impl": "reference", "metric": "IQ Msamples/s", "value": round(agg, 3), "unit": "Msamples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": warm,
         "ms_per_step": round(1e3 * statistics.mean(v[2] for v in vals), 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 NCO / int32 accumulate / int8 out", "data": "synthetic",
         "config": workload_config(nchan, args.iq16, args.gpus),
@@ -283,6 +295,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    note("device %d of %d ranks, %d blocks x %d channels" % (local, world, args.blocks, args.chan))
     nchan, nblk = args.chan, args.blocks
     ss = gps.SC16 if args.iq16 else gps.SC08
     bytes_per_sample = 4 if args.iq16 else 2
@@ -305,12 +318,14 @@ def main():
     assert sh != 0
 
     # ---- resident-input run: parameters + carrier chain uploaded once, kernels replayed ----
+    note("resident-input leg: first full pass")
     ctx.synth_blocks_device(chans, ss, out_dev.data_ptr(), stream=sh)
     torch.cuda.synchronize()
     sampler = None
     if rank == 0:
         uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
         sampler = ClockSampler(local, uuid)
+    note("resident-input leg: %d warm-up + %d timed steps" % (args.warmup, args.steps))
     for _ in range(args.warmup):
         ctx.replay_device(out_dev.data_ptr(), sh, 15)
     torch.cuda.synchronize()
@@ -342,26 +357,42 @@ def main():
     value = samples_all / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the blocking C-ABI call, host buffers --------------------------
-    out_host = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, pin_memory=True)
-    out_np = out_host.numpy()
-    e2e_steps = max(3, min(args.steps, 8))      # ~38 ms each; PCIe throughput varies by a few % run to run
-    stats = None
-    for _ in range(1):
-        ctx.synth_blocks(chans, ss, out=out_np)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_each = []
-    for _ in range(e2e_steps):
-        t1 = time.perf_counter()
-        _, _, stats = ctx.synth_blocks(chans, ss, out=out_np, want_stats=True)
-        e2e_each.append(time.perf_counter() - t1)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_value = samples_all / e2e_s / 1e6
-    # result check: the end-to-end output equals the resident-input output (same bytes)
-    same = bool(torch.equal(out_host.cuda(), out_dev))
-    same = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
+    note("value leg done: %.3f ms per step; end-to-end leg (pinned host buffer %.2f GB)" % (
+        ms_per_step, nblk * gps.BLOCK_ELEMS * (2 if args.iq16 else 1) / 1e9))
+    e2e, e2e_err = None, None
+    try:
+        out_host = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, pin_memory=True)
+        out_np = out_host.numpy()
+        e2e_steps = max(3, min(args.steps, 8))      # ~38 ms each; PCIe throughput varies by a few % run to run
+        stats = None
+        for _ in range(1):
+            ctx.synth_blocks(chans, ss, out=out_np)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_each = []
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            _, _, stats = ctx.synth_blocks(chans, ss, out=out_np, want_stats=True)
+            e2e_each.append(time.perf_counter() - t1)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_s = max_over_ranks(e2e_s)
+        e2e_value = samples_all / e2e_s / 1e6
+        # result check: the end-to-end output equals the resident-input output (same bytes)
+        same = bool(torch.equal(out_host.cuda(), out_dev))
+        same = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
+        e2e = {"value": round(e2e_value, 1), "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(stats.h2d_bytes) * 1, "d2h_bytes_per_step": int(stats.d2h_bytes),
+               "ms_per_step": round(e2e_s * 1e3, 2), "steps": e2e_steps,
+               "ms_best_step_rank0": round(min(e2e_each) * 1e3, 2), "host_chain_ms": round(stats.host_chain_ms, 2),
+               "chain_fallbacks": int(stats.chain_fallbacks), "kernel_launches_per_step": int(stats.launches),
+               "host_threads": host_threads, "numa_node": numa_node,
+               "timing": "wall clock around the blocking call, max over ranks",
+               "output_equals_resident_run": same}
+        del out_host, out_np
+    except Exception as ex:                      # the line is still printed, with the reason
+        e2e_err = "%s: %s" % (type(ex).__name__, ex)
+        note("end-to-end leg failed: " + e2e_err)
 
     gather_ms = None
     if args.gather and world > 1:
@@ -396,19 +427,18 @@ def main():
                          "peak_source": peak_src,
                          "note": "path is issue-slot / shared-memory bound (~13.9 SASS instructions per 32-channel "
                                  "sample step), not HBM bound; see DESIGN.md and profiles/"},
-            "e2e": {"value": round(e2e_value, 1), "unit": "Msamples/s",
-                    "h2d_bytes_per_step": int(stats.h2d_bytes) * 1, "d2h_bytes_per_step": int(stats.d2h_bytes),
-                    "ms_per_step": round(e2e_s * 1e3, 2), "steps": e2e_steps,
-                    "ms_best_step_rank0": round(min(e2e_each) * 1e3, 2), "host_chain_ms": round(stats.host_chain_ms, 2),
-                    "chain_fallbacks": int(stats.chain_fallbacks), "kernel_launches_per_step": int(stats.launches),
-                    "host_threads": host_threads, "numa_node": numa_node, "timing": "wall clock around the blocking call, max over ranks",
-                    "output_equals_resident_run": same},
+            "e2e": e2e if e2e is not None else {"value": None, "unit": "Msamples/s", "error": e2e_err},
             "slice_seed_s": round(t_seed, 3),
         }
         if gather_ms is not None:
             line["nccl_all_gather_ms"] = round(gather_ms, 3)
         if not args.no_cpu_baseline and world == 1:
-            r = run_reference_cpu(nchan, 10.0 if nchan <= 12 else 5.0, 1)
+            note("cpu_baseline leg: one copy of the reference producer")
+            try:
+                r = run_reference_cpu(nchan, 10.0 if nchan <= 12 else 5.0, 1)
+            except Exception as ex:
+                r = None
+                line["cpu_baseline"] = {"value": None, "error": "%s: %s" % (type(ex).__name__, ex)}
             if r is not None:
                 line["cpu_baseline"] = {
                     "value": round(r[0], 3), "unit": "Msamples/s", "cores": 1, "kind": "reference",

@@ -27,3 +27,18 @@ def start_phases(chans_prefix, carr_phase0=None, threads=16, ctx=None):
     if ctx is not None:          # parallel-in-time on the rank's own GPU: milliseconds instead of seconds
         return ctx.carrier_chain(chans_prefix, carr_phase0)
     return api.carrier_chain(chans_prefix, carr_phase0, threads)
+
+
+def seed_slice(chans_slice, prefix_last_row, phases):
+    """Seed the first block of a rank's slice: a slot CONTINUES the carrier phase chained through the
+    preceding blocks (`phases`, from start_phases) only where it still holds the satellite it held in the
+    block before the slice (`prefix_last_row`, the chans row of block lo-1); a slot that is (re)allocated
+    exactly at the slice edge keeps the allocation phase the scenario put into carr_phase
+    (allocateChannel, gps.c:2203-2210) -- the same rule gpsb200_synth_blocks applies between the blocks of
+    one call. Returns a copy of chans_slice."""
+    out = np.array(chans_slice, copy=True)
+    if prefix_last_row is None or out.shape[0] == 0:
+        return out
+    keep = (out["prn"][0] > 0) & (out["prn"][0] == prefix_last_row["prn"])
+    out["carr_phase"][0] = np.where(keep, phases, out["carr_phase"][0])
+    return out

@@ -24,6 +24,7 @@
 #include <string.h>
 #include <time.h>
 #include <pthread.h>
+#include <zlib.h>
 
 /* First inclusion of the reference headers fixes their include guards. */
 #include "gps.h"
@@ -48,6 +49,7 @@ typedef struct {
 
 static FILE *g_params;
 static FILE *g_iq;
+static FILE *g_crc;   /* --crc: one CRC-32 (zlib) per enqueued buffer instead of the bytes (long runs) */
 static uint32_t g_blocks;
 static uint32_t g_sample_size;
 static struct timespec g_t0, g_t1;
@@ -125,6 +127,12 @@ void fifo_enqueue(struct iq_buf *buf) {
         if (g_sample_size == SC16) fwrite(buf->data16, 2, buf->validLength, g_iq);
         else fwrite(buf->data8, 1, buf->validLength, g_iq);
     }
+    if (g_crc) {
+        const size_t nbytes = (size_t) buf->validLength * (g_sample_size == SC16 ? 2 : 1);
+        const uint32_t c = (uint32_t) crc32(0L, g_sample_size == SC16 ? (const Bytef *) buf->data16 : (const Bytef *) buf->data8,
+                                            (uInt) nbytes);
+        fwrite(&c, 4, 1, g_crc);
+    }
     g_blocks++;
 }
 
@@ -134,13 +142,13 @@ int thread_to_core(int core_id) { (void) core_id; return 0; }
 static void usage(void) {
     fprintf(stderr,
             "ref_dump -e NAV -l lat,lon,h -d SEC [--iq16] [-m motion.csv] [-s y/m/d,h:m:s]\n"
-            "         [--iq FILE] [--params FILE]\n");
+            "         [--iq FILE] [--crc FILE] [--params FILE] [-3] [--pluto-gain]\n");
     exit(2);
 }
 
 int main(int argc, char **argv) {
     static simulator_t sim; /* zero-initialised like gps-sim.c's global */
-    const char *iq_name = NULL, *par_name = NULL;
+    const char *iq_name = NULL, *par_name = NULL, *crc_name = NULL;
     double dur = 10.0;
 
     sim.ionosphere_enable = true;
@@ -165,6 +173,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--pluto-gain")) sim.sdr_type = SDR_PLUTOSDR;
         else if (!strcmp(argv[i], "--iq") && i + 1 < argc) iq_name = argv[++i];
         else if (!strcmp(argv[i], "--params") && i + 1 < argc) par_name = argv[++i];
+        else if (!strcmp(argv[i], "--crc") && i + 1 < argc) crc_name = argv[++i];
         else usage();
     }
     if (!sim.nav_file_name) usage();
@@ -177,6 +186,7 @@ int main(int argc, char **argv) {
 
     if (iq_name && !(g_iq = fopen(iq_name, "wb"))) { perror(iq_name); return 1; }
     if (par_name && !(g_params = fopen(par_name, "wb"))) { perror(par_name); return 1; }
+    if (crc_name && !(g_crc = fopen(crc_name, "wb"))) { perror(crc_name); return 1; }
     memset(g_last_prn, 0, sizeof g_last_prn);
 
     struct { uint32_t version, max_chan, sample_size, samples_per_block; } hdr =
@@ -198,6 +208,7 @@ int main(int argc, char **argv) {
     put_rec(TAG_END, &end, sizeof end);
     if (g_iq) fclose(g_iq);
     if (g_params) fclose(g_params);
+    if (g_crc) fclose(g_crc);
     /* One machine-readable line for bench.py / tests. */
     printf("{\"blocks\": %u, \"samples\": %llu, \"producer_seconds\": %.6f, \"max_chan\": %d, \"sample_size\": %d}\n",
            g_blocks, (unsigned long long) g_blocks * (TX_SAMPLERATE / 10), secs, MAX_CHAN, (int) sim.sample_size);

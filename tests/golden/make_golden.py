@@ -49,6 +49,11 @@ SCENARIOS = {
     # two ephemeris sets (02:00 and 04:00), start 02:55:00: the reference rolls to the second set at the first
     # 30 s boundary after 03:00:00 (gps.c:2890-2905) and rebuilds every channel's subframes. 400 s, 12 channels.
 SCENARIOS["sky12_ephroll_400s_i8"] = (12, "ref_dump12", 400, [], [])
+# BASELINE configs[3] LITERALLY: the reference's own circle.csv, --iq16, 60 s (599 blocks). The motion rows the run
+# consumed travel inside the fixture (the GPU box has no /root/reference): tests re-write them with %.17g.
+SCENARIOS["sky12_circle_60s_i16"] = (12, "ref_dump12", 60, ["--iq16", "-m", "/root/reference/circle.csv"], [])
+# ADALM-Pluto flavour of the sample loop: gain x 2 (gps.c:2759-2763), int16 (sdr_pluto.c:107-110)
+SCENARIOS["sky12_pluto_3s_i16"] = (12, "ref_dump12", 3, ["--iq16", "--pluto-gain"], [0])
 LOCS = {"sky32_lat60_310s_i8": "60.0,140.0,0.0"}
 STARTS = {"sky12_ephroll_400s_i8": "2024/01/07,02:55:00"}
 RINEX_ARGS = {"sky12_ephroll_400s_i8": ["--sets", "2"]}
@@ -109,11 +114,47 @@ def run(name):
         out["nav_frames"] = np.stack(frames)
         out["nav_frame_of_block"] = idx
         out.update(extra_out)
+        if "/root/reference/circle.csv" in extra:
+            rows = np.loadtxt("/root/reference/circle.csv", delimiter=",")
+            out["motion_rows"] = rows[:int(secs * 10)]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "blocks", nblk, "chan", p["max_chan"], "frames", len(frames),
               "active", int((ch["prn"][0] > 0).sum()))
 
 
+def run_crc_only(name, nsat, binary, secs, crc_file=None):
+    """Long runs: only the CRC-32 of every enqueued block is kept (ref_dump --crc); parameters come from
+    the scenario engine in the test. crc_file: reuse the output of an earlier (background) run of exactly
+    this command line."""
+    with tempfile.TemporaryDirectory() as td:
+        if crc_file is None:
+            nav = os.path.join(td, "sky.nav")
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "gen_rinex.py"),
+                                   "--nsat", str(nsat), "--out", nav])
+            crc_file = os.path.join(td, "crc.bin")
+            subprocess.check_call([os.path.join(REF, binary), "-e", nav, "-l", LOC, "-d", str(secs), "-s", START,
+                                   "--crc", crc_file], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+        crcs = np.fromfile(crc_file, dtype="<u4")
+    assert crcs.size == int(secs * 10 + 0.5) - 1, crcs.size
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), crcs=crcs, max_chan=np.int32(nsat), sample_size=np.int32(1),
+                        seconds=np.int32(secs))
+    print(name, "blocks", crcs.size)
+
+
+# BASELINE configs[4]: 32 channels, int8, 3600 s (35 999 blocks). The -O2 build of the unmodified reference
+# (byte-identical output, see oracle/Makefile) needs ~25 min of one CPU for it.
+CRC_ONLY = {"sky32_static_3600s_i8": (32, "ref_run32_fast", 3600)}
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or SCENARIOS):
-        run(n)
+    args = sys.argv[1:]
+    crc_file = None
+    if "--crc-file" in args:
+        i = args.index("--crc-file")
+        crc_file = args[i + 1]
+        del args[i:i + 2]
+    for n in (args or list(SCENARIOS) + list(CRC_ONLY)):
+        if n in CRC_ONLY:
+            run_crc_only(n, *CRC_ONLY[n], crc_file=crc_file)
+        else:
+            run(n)

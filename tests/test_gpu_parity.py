@@ -438,3 +438,90 @@ def test_randomized_differential_vs_oracle():
             out, cp = ctx.synth_blocks(ch, ss)
         assert np.array_equal(out, want), (case, nchan, ss, scale)
         assert np.array_equal(cp, carr), case
+
+
+def test_config3_literally_circle_csv_int16_60s_from_rinex(tmp_path):
+    """BASELINE configs[3] LITERALLY: the reference's own circle.csv (rows carried in the fixture, re-written with
+    %.17g so that every double parses back identically), --iq16, 60 s = 599 blocks: RINEX + motion file in,
+    the reference's int16 stream out."""
+    g = scenario.load_golden("sky12_circle_60s_i16")
+    mot = tmp_path / "circle.csv"
+    with open(mot, "w") as f:
+        for r in g["motion_rows"]:
+            f.write("%.17g,%.17g,%.17g,%.17g\n" % tuple(r))
+    ch, nav = gps.scenario(_nav_file(tmp_path, 12), 35.681298, 139.766247, 10.0, seconds=60, max_chan=12,
+                           motion_file=str(mot), start=(2024, 1, 7, 2, 0, 0.0))
+    assert ch.shape == (599, 12)
+    for f in ("prn", "f_carr", "f_code", "code_phase", "gain", "iword", "ibit", "icode"):     # first two blocks: dumped
+        assert np.array_equal(ch[f][:2], g["chans"][f]), f
+    with gps.Context(12, 599, max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 2)
+    bad = np.nonzero(scenario.crc_blocks(out) != g["crcs"][:, 0])[0]
+    assert bad.size == 0, bad[:10]
+
+
+def test_pluto_gain_int16_matches_reference_stream(tmp_path):
+    """ADALM-Pluto flavour of the loop: gain x 2 (gps.c:2759-2763), int16 (sdr_pluto.c:107-110). Once from the
+    reference's dumped parameters, once from the RINEX file through the scenario engine (pluto_gain=True)."""
+    g, out = run_golden("sky12_pluto_3s_i16")
+    assert np.array_equal(out[:gps.BLOCK_ELEMS], g["keep_blocks"][0])
+    ch, nav = gps.scenario(_nav_file(tmp_path, 12), 35.681298, 139.766247, 10.0, seconds=3, max_chan=12,
+                           start=(2024, 1, 7, 2, 0, 0.0), pluto_gain=True)
+    assert np.array_equal(ch["gain"], g["chans"]["gain"])
+    with gps.Context(12, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out2, _ = ctx.synth_blocks(ch, 2)
+    assert np.array_equal(scenario.crc_blocks(out2), g["crcs"][:, 0])
+
+
+def test_rinex3_file_to_reference_stream(tmp_path):
+    """RINEX-3 navigation file (readRinex3, gps.c:1512-1891) -> scenario engine -> CUDA synthesis == the reference's
+    stream for the same file read with -3."""
+    import os
+    import subprocess
+    import sys
+    g = scenario.load_golden("sky12_rinex3_3s_i8")
+    nav_file = tmp_path / "sky12.rnx"
+    subprocess.check_call([sys.executable, os.path.join(scenario.ROOT, "oracle", "gen_rinex.py"), "--nsat", "12", "--v3",
+                           "--out", str(nav_file)])
+    ch, nav = gps.scenario(str(nav_file), 35.681298, 139.766247, 10.0, seconds=3, max_chan=12,
+                           start=(2024, 1, 7, 2, 0, 0.0), rinex3=True)
+    with gps.Context(12, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 1)
+    assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
+
+
+def _sliced_stream_crcs(ch, nav, edges, sample_size=1):
+    """Synthesize one scenario as len(edges)-1 time slices, each by its own context ("rank"), sequentially on
+    this device: a rank knows only the parameters and the exact carrier phases handed over by the chain through the
+    blocks before its slice (sharding.start_phases / seed_slice) -- never another rank's output."""
+    crcs = []
+    nchan = ch.shape[1]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        with gps.Context(nchan, hi - lo, max_nav_frames=len(nav)) as ctx:
+            ctx.set_nav_frames(nav)
+            part = ch[lo:hi]
+            if lo > 0:
+                part = gps.sharding.seed_slice(part, ch[lo - 1], gps.sharding.start_phases(ch[:lo], ctx=ctx))
+            out, _ = ctx.synth_blocks(part, sample_size)
+            crcs.append(scenario.crc_blocks(out))
+    return np.concatenate(crcs)
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_time_sliced_stream_equals_reference_stream(ranks, tmp_path):
+    """SURVEY section 8e on one device: the 310 s / 32-channel reallocation scenario cut into K slices, every slice
+    made by a separate context from the hand-over phases alone; the concatenation is the reference's stream. One
+    extra cut is placed exactly on the block where a satellite rises into a free slot (block 2399/2400: the slot
+    must take its allocation phase, not a chained one) and one where a satellite sets."""
+    g = scenario.load_golden("sky32_lat60_310s_i8")
+    ch, nav = gps.scenario(_nav_file(tmp_path, 32), 60.0, 140.0, 0.0, seconds=310, max_chan=32, start=(2024, 1, 7, 2, 0, 0.0))
+    occ = ch["prn"]
+    change = [b for b in range(1, ch.shape[0]) if np.any(occ[b] != occ[b - 1])]
+    assert change, "the scenario is expected to reallocate"
+    edges = sorted(set([gps.sharding.slice_bounds(ch.shape[0], ranks, r)[0] for r in range(ranks)] + change + [ch.shape[0]]))
+    got = _sliced_stream_crcs(ch, nav, edges)
+    bad = np.nonzero(got != g["crcs"][:, 0])[0]
+    assert bad.size == 0, (edges, bad[:10])

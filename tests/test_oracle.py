@@ -122,3 +122,16 @@ def test_oracle_blocks_around_reallocation_and_ephemeris_roll(name, blocks):
         chans = oracle_lib.make_chans(row, frames[fidx[b]])
         out = oracle_lib.quantize8(oracle_lib.synth_block(chans))
         assert zlib.crc32(out.tobytes()) == crcs[b, 0], (name, b)
+
+
+def test_oracle_pluto_gain_int16_bit_exact():
+    """ADALM-Pluto flavour: gain x 2 (gps.c:2759-2763), int16 stream; all 29 blocks."""
+    g = run_scenario("sky12_pluto_3s_i16")
+    assert float(g["chans"]["gain"].max()) > 1.2          # doubled gains really are in the fixture
+    chans = oracle_lib.make_chans(g["chans"][0], g["nav_frames"][0])
+    assert np.array_equal(oracle_lib.synth_block(chans), g["keep_blocks"][0])
+
+
+def test_oracle_config3_circle_60s_first_blocks():
+    """configs[3] literally (circle.csv, --iq16, 60 s): the fixture keeps the first two blocks' parameters."""
+    run_scenario("sky12_circle_60s_i16", nblocks=2)

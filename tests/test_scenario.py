@@ -18,6 +18,7 @@ CASES = {
     "sky32_static_10s_i8": dict(nsat=32, chan=32, secs=10),
     "sky12_circle_10s_i16": dict(nsat=12, chan=12, secs=10, motion=True),
     "sky12_rinex3_3s_i8": dict(nsat=12, chan=12, secs=3, v3=True),
+    "sky12_pluto_3s_i16": dict(nsat=12, chan=12, secs=3, pluto=True),
 }
 
 
@@ -45,7 +46,8 @@ def test_scenario_engine_matches_reference_dump_bit_for_bit(name, tmp_path):
     want, frames = scenario.golden_chans(g)
     mot = motion_file(tmp_path) if c.get("motion") else None
     got, nav = gps.scenario(make_nav(tmp_path, c["nsat"], c.get("v3", False)), *LOC, seconds=c["secs"],
-                            max_chan=c["chan"], motion_file=mot, start=START, rinex3=c.get("v3", False))
+                            max_chan=c["chan"], motion_file=mot, start=START, rinex3=c.get("v3", False),
+                            pluto_gain=c.get("pluto", False))
     assert got.shape == want.shape
     assert np.array_equal(got["prn"], want["prn"])
     act = want["prn"] > 0
@@ -138,3 +140,21 @@ def test_rinex_version_flag_must_match_the_file(tmp_path):
         gps.scenario(make_nav(tmp_path, 12, v3=True), *LOC, seconds=3, start=START)            # v3 file, v2 reader
     with pytest.raises(gps.GpsB200Error):
         gps.scenario(make_nav(tmp_path, 12), *LOC, seconds=3, start=START, rinex3=True)         # v2 file, v3 reader
+
+
+def test_config3_circle_csv_60s_engine_matches_dump(tmp_path):
+    """configs[3] literally: the reference's circle.csv rows (carried in the fixture, re-written with %.17g) for 60 s;
+    the first two blocks' parameters are in the fixture, the whole run is compared on the GPU box."""
+    g = scenario.load_golden("sky12_circle_60s_i16")
+    mot = tmp_path / "circle.csv"
+    with open(mot, "w") as f:
+        for r in g["motion_rows"]:
+            f.write("%.17g,%.17g,%.17g,%.17g\n" % tuple(r))
+    got, nav = gps.scenario(make_nav(tmp_path, 12), *LOC, seconds=60, max_chan=12, motion_file=str(mot), start=START)
+    assert got.shape == (599, 12)
+    for f in ("prn", "iword", "ibit", "icode", "f_carr", "f_code", "code_phase", "gain"):
+        assert np.array_equal(got[f][:2], g["chans"][f]), f
+    src = "/root/reference/circle.csv"
+    if os.path.exists(src):            # the re-written rows parse to the same doubles as the original file
+        ref, _ = gps.scenario(make_nav(tmp_path, 12), *LOC, seconds=60, max_chan=12, motion_file=src, start=START)
+        assert got.tobytes() == ref.tobytes()
