@@ -128,6 +128,52 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
                                 int sample_size, void *dst_device, void *stream,
                                 double *carr_phase_out, gpsb200_stats_t *stats);
 
+/* ---- time-slice hand-over (multi-GPU: rank r makes blocks [lo_r, hi_r) of ONE stream) -----------------
+ * The only state a slice needs from the blocks before it is each slot's exact carrier phase (gps.c:2821-2826
+ * never resets carr_phase). Its resolution is parallel in time (block probes on the GPU chained per span, then
+ * one host step per span), so a rank can do almost all of it before the incoming phases exist. One device-path
+ * call is therefore offered in three steps:
+ *   1. gpsb200_slice_prepare  host records, parameters up, carrier tables; fills *link: how this slice maps an
+ *                             incoming chain state to the (closed-form, GUESSED) outgoing one. Ranks exchange
+ *                             their links and compose them with gpsb200_link_apply() to obtain good guesses of
+ *                             their incoming state without any GPU work.
+ *   2. gpsb200_slice_probe    incoming state as GUESSED (NULL: the slice starts the stream): speculative block
+ *                             probes + span chaining are enqueued.
+ *   3. gpsb200_slice_finish   incoming state EXACT (prn_in/phase_in, from the previous rank's *_out; NULL: the
+ *                             stream starts here): host scan over the span summaries, run checkpoints with the
+ *                             device self-check, synthesis enqueued on the stream. prn_out/phase_out (exact state
+ *                             after the slice) are valid on return -- BEFORE the synthesis has run -- and are what
+ *                             the next rank's gpsb200_slice_finish takes.
+ * A slot continues the incoming phase only when it still holds the same satellite (prn_in[c] == prn of its first
+ * block, > 0); otherwise its first block takes carr_phase from chans, exactly as between the blocks of one call.
+ * chans must stay valid until gpsb200_slice_prepare returns. gpsb200_synth_blocks_device == the three steps with
+ * NULL incoming states. */
+typedef struct gpsb200_slice_link {
+    int32_t prn_first[GPSB200_MAX_CHAN];    /* satellite of each slot in the slice's first block (0: idle) */
+    int32_t prn_last[GPSB200_MAX_CHAN];     /* ... in its last block */
+    int32_t reset_inside[GPSB200_MAX_CHAN]; /* 1: the slot was (re)allocated or idle inside the slice: value is absolute */
+    double first_phase[GPSB200_MAX_CHAN];   /* carr_phase of the first block (used when the slot does not continue) */
+    double value[GPSB200_MAX_CHAN];         /* guessed phase after the slice (absolute), or the advance over the slice */
+} gpsb200_slice_link_t;
+/* dst_device and/or dst_host: with dst_host != NULL the synthesis is launched in chunks whose downloads into dst_host
+ * (pinned memory) overlap later chunks, dst_device may then be NULL (a context-owned staging buffer is used);
+ * gpsb200_slice_wait blocks until synthesis and downloads of the slice are complete. */
+int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
+                          void *dst_device, void *dst_host, void *stream, gpsb200_slice_link_t *link);
+int gpsb200_slice_wait(gpsb200_ctx_t *ctx);
+int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in);
+int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
+                         double *phase_out, gpsb200_stats_t *stats);
+/* Host only: the link of a slice from its parameters alone (identical to what gpsb200_slice_prepare fills). */
+int gpsb200_slice_link_host(const gpsb200_chan_t *chans, int nblk, int nchan, gpsb200_slice_link_t *link);
+/* Host only: (prn_in, phase_in) -> guessed (prn_out, phase_out) after the slice `link` describes. */
+int gpsb200_link_apply(const gpsb200_slice_link_t *link, int nchan, const int32_t *prn_in, const double *phase_in,
+                       int32_t *prn_out, double *phase_out);
+
+/* Test hook of the device self-check: corrupt the resolved carrier chain of the next calls by one unit of the
+ * rounding grid (on != 0); every synth call must then fail with GPSB200_ERR_INTERNAL instead of returning samples. */
+int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on);
+
 /* Re-run the device part of the previous gpsb200_synth_blocks_device call (parameters,
  * start phases and guesses already resident in HBM): used by bench.py to time the kernels
  * alone. kernel_mask bits: 8 = carrier tables, 4 = carrier probe, 1 = run checkpoints, 2 = synthesis. */
@@ -158,6 +204,13 @@ int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans
  * accepted (then *end_out == gpsb200_carrier_advance(start, ...), bit for bit), 0 when it is
  * rejected (the pipeline then walks that block sequentially). For tests. */
 int gpsb200_carrier_probe_fixup(double start, double guess, double f_carr, int64_t nsamples, double *end_out);
+
+/* Host-only model of the two-level (span) resolution of the chain for one satellite over nblk blocks with Doppler
+ * f_carr[j]: block probes from guesses derived from start_guess, speculative chaining of the span for both parity
+ * variants, ONE fix-up with the true start. Returns 1 and the exact start phase of every block plus the end phase
+ * (starts_out[nblk + 1]) when the span-level speculation is accepted, 0 when it is rejected (the pipeline then
+ * resolves the span block by block). For tests. */
+int gpsb200_span_chain_host(const double *f_carr, int nblk, double start_true, double start_guess, double *starts_out);
 
 /* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);

@@ -52,6 +52,12 @@ class ScenarioConfig(C.Structure):
                 ("start_sec", C.c_double)]
 
 
+class SliceLink(C.Structure):
+    """gpsb200_slice_link_t."""
+    _fields_ = [("prn_first", C.c_int32 * 32), ("prn_last", C.c_int32 * 32), ("reset_inside", C.c_int32 * 32),
+                ("first_phase", C.c_double * 32), ("value", C.c_double * 32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("host_chain_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("checkpoint_kernel_ms", C.c_double), ("synth_kernel_ms", C.c_double),
@@ -65,7 +71,8 @@ _lib = None
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
-           "gpsb200_codegen", "gpsb200_bind_numa",
+           "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_slice_prepare", "gpsb200_slice_probe",
+           "gpsb200_slice_finish", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
            "gpsb200_scenario_chans", "gpsb200_scenario_nav",
@@ -107,6 +114,15 @@ def lib():
         L.gpsb200_carrier_probe_fixup.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_double)]
         L.gpsb200_carrier_chain_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gpsb200_carrier_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.gpsb200_span_chain_host.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.gpsb200_slice_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.POINTER(SliceLink)]
+        L.gpsb200_slice_wait.argtypes = [C.c_void_p]
+        L.gpsb200_slice_link_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceLink)]
+        L.gpsb200_slice_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gpsb200_slice_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        L.gpsb200_link_apply.argtypes = [C.POINTER(SliceLink), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gpsb200_debug_corrupt_chain.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -142,6 +158,39 @@ def carrier_chain(chans, phase_in=None, threads=16):
     if rc:
         raise GpsB200Error(rc, "gpsb200_carrier_chain")
     return out
+
+
+def span_chain_host(f_carr, start_true, start_guess):
+    """Host model of the two-level chain for one span. -> float64[nblk + 1] exact block starts + end, or None if
+    the span-level speculation was rejected."""
+    f = np.ascontiguousarray(f_carr, dtype=np.float64)
+    out = np.zeros(f.size + 1)
+    rc = lib().gpsb200_span_chain_host(f.ctypes.data, f.size, float(start_true), float(start_guess), out.ctypes.data)
+    if rc < 0:
+        raise GpsB200Error(rc, "gpsb200_span_chain_host")
+    return out if rc == 1 else None
+
+
+def slice_link_host(chans):
+    """gpsb200_slice_link_host: the closed-form link of a slice (host only). -> SliceLink"""
+    a = np.ascontiguousarray(chans, dtype=CHAN_DTYPE)
+    link = SliceLink()
+    rc = lib().gpsb200_slice_link_host(a.ctypes.data, a.shape[0], a.shape[1], C.byref(link))
+    if rc:
+        raise GpsB200Error(rc, "gpsb200_slice_link_host")
+    return link
+
+
+def link_apply(link, nchan, prn_in=None, phase_in=None):
+    """gpsb200_link_apply -> (prn_out int32[nchan], phase_out float64[nchan])."""
+    pi = None if prn_in is None else np.ascontiguousarray(prn_in, dtype=np.int32)
+    xi = None if phase_in is None else np.ascontiguousarray(phase_in, dtype=np.float64)
+    po, xo = np.zeros(nchan, np.int32), np.zeros(nchan, np.float64)
+    rc = lib().gpsb200_link_apply(C.byref(link), nchan, None if pi is None else pi.ctypes.data,
+                                  None if xi is None else xi.ctypes.data, po.ctypes.data, xo.ctypes.data)
+    if rc:
+        raise GpsB200Error(rc, "gpsb200_link_apply")
+    return po, xo
 
 
 def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None, start=None,
@@ -246,6 +295,42 @@ class Context:
                                                       C.c_void_p(dst_ptr), C.c_void_p(stream), cp.ctypes.data,
                                                       C.byref(st) if want_stats else None))
         return (cp, st) if want_stats else cp
+
+    def slice_prepare(self, chans, sample_size, dst_ptr=0, stream=0, dst_host=None):
+        """Step 1 of the time-slice hand-over. dst_ptr: raw device pointer and/or dst_host: numpy array in pinned
+        memory. -> SliceLink"""
+        a = self._chans(chans)
+        nblk, nchan = a.shape
+        link = SliceLink()
+        hp = None if dst_host is None else C.c_void_p(dst_host.ctypes.data)
+        self._check(lib().gpsb200_slice_prepare(self._h, a.ctypes.data, nblk, nchan, sample_size, C.c_void_p(dst_ptr),
+                                                hp, C.c_void_p(stream), C.byref(link)))
+        self._slice_nchan = nchan
+        return link
+
+    def slice_probe(self, prn_in=None, phase_guess_in=None):
+        pi = None if prn_in is None else np.ascontiguousarray(prn_in, dtype=np.int32)
+        xi = None if phase_guess_in is None else np.ascontiguousarray(phase_guess_in, dtype=np.float64)
+        self._check(lib().gpsb200_slice_probe(self._h, None if pi is None else pi.ctypes.data,
+                                              None if xi is None else xi.ctypes.data))
+
+    def slice_finish(self, prn_in=None, phase_in=None, want_stats=False):
+        """Step 3. -> (prn_out, phase_out[, Stats]): the exact chain state after the slice."""
+        n = self._slice_nchan
+        pi = None if prn_in is None else np.ascontiguousarray(prn_in, dtype=np.int32)
+        xi = None if phase_in is None else np.ascontiguousarray(phase_in, dtype=np.float64)
+        po, xo = np.zeros(n, np.int32), np.zeros(n, np.float64)
+        st = Stats()
+        self._check(lib().gpsb200_slice_finish(self._h, None if pi is None else pi.ctypes.data,
+                                               None if xi is None else xi.ctypes.data, po.ctypes.data, xo.ctypes.data,
+                                               C.byref(st)))
+        return (po, xo, st) if want_stats else (po, xo)
+
+    def slice_wait(self):
+        self._check(lib().gpsb200_slice_wait(self._h))
+
+    def debug_corrupt_chain(self, on):
+        self._check(lib().gpsb200_debug_corrupt_chain(self._h, 1 if on else 0))
 
     def carrier_chain(self, chans, phase_in=None):
         """Exact carrier phases after all blocks of chans (device probe + host fix-up, no synthesis)."""

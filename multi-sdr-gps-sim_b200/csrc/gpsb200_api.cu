@@ -40,6 +40,7 @@ constexpr int kSynthChunk = 256;   // blocks per synthesis launch of the host-de
 constexpr int kSegFirst = 256;     // first carrier-chain segment of the host-destination path: small, so
                                    // that the download can start early ...
 constexpr int kSegBlocks = 1024;   // ... later ones larger (their probe kernels are latency bound)
+constexpr int kSpanBlocks = 32;    // blocks per span of the two-level carrier chain (nco_exact.h: span_chain)
 
 struct ChainState {
     int prn = 0;
@@ -117,7 +118,6 @@ private:
 struct gpsb200_ctx {
     gpsb200_config_t cfg{};
     int nruns = 0;
-    int units = 1, unit_samples = GPSB200_BLOCK_SAMPLES;   // carrier-chain units per block
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> ev_done;      // one per synthesis chunk
@@ -129,8 +129,24 @@ struct gpsb200_ctx {
     double *d_carr_end = nullptr;
     int *d_chain_errors = nullptr, *h_chain_errors = nullptr;   // device self-check of the carrier chain
     double *d_guess = nullptr, *h_guess = nullptr;     // speculative block-start phases
-    double *d_carr0 = nullptr, *h_carr0 = nullptr;     // exact block-start phases
-    CarrierProbe *d_probe = nullptr, *h_probe = nullptr;
+    std::vector<uint8_t> h_guess_abs;                  // relative-mode marker per (block, channel), see prepare_blocks
+    double *d_carr0 = nullptr, *h_carr0 = nullptr;     // exact block-start phases of host-resolved (irregular) spans
+    CarrierProbe *d_probe = nullptr;                   // block probes in HBM (k_chain reads them)
+    CarrierProbe *h_probe = nullptr, *d_probe_host = nullptr;   // ... and in mapped host memory (host fallback)
+    CarrierProbe *h_span_sum = nullptr, *d_span_sum = nullptr;  // span summaries, mapped host memory
+    SpanBlockState *d_spec = nullptr;                  // speculative block-start phases
+    SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
+    int max_spans = 0;
+    bool fault_inject_chain = false;       // gpsb200_debug_corrupt_chain(): test hook of the device self-check
+    // state of a begun, not yet finished call (gpsb200_synth_begin / _finish)
+    struct Pending {
+        bool active = false;
+        int nblk = 0, nchan = 0, sample_size = 0;
+        void *dst = nullptr, *dst_host = nullptr;
+        cudaStream_t stream = nullptr;
+        bool probed = false;
+        gpsb200_stats_t st{};
+    } pending;
     void *d_out = nullptr;
     size_t out_bytes = 0;
     bool nav_dirty = true;
@@ -142,6 +158,14 @@ struct gpsb200_ctx {
 };
 
 namespace {
+
+struct OneSatellite {          // parameter accessor of span_chain() for the host model: one satellite, increments cc[j]
+    const double *cc;
+    __host__ __device__ void operator()(int j, double &c, int32_t &prn) const {
+        c = cc[j];
+        prn = 1;
+    }
+};
 
 int fail(gpsb200_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
@@ -162,22 +186,35 @@ double now_ms() {
 
 // Host pre-pass: validate, fill the device-layout records and GUESS every block's start
 // carrier phase (closed form + expected rounding drift, long double accumulation).
+// With link != NULL (time-slice hand-over, gpsb200_slice_prepare) the incoming chain state is not known yet:
+// guesses are accumulated RELATIVE to it (h_guess holds the advance since the slice start, h_guess_abs marks
+// blocks after a (re)allocation inside the slice, whose guesses are absolute) and finalize_guesses() adds the
+// offset later; *link describes how the slice maps an incoming state to the guessed outgoing one.
 int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
-                   const std::vector<ChainState> &chain) {
+                   const std::vector<ChainState> &chain, gpsb200_slice_link_t *link = nullptr) {
     const double delt = 1.0 / (double) GPSB200_SAMPLERATE;     // gps.c:2298
     std::vector<int> status(nchan, GPSB200_OK);
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
             long double acc = chain[c].phase;               // exact phase after block b0-1 (if any)
             int prev_prn = chain[c].prn;                    // 0 at the start of a call: block 0 is "fresh"
+            bool absolute = link == nullptr;                // relative mode: true once a slot was (re)allocated
+            if (link) {
+                acc = 0.0L;
+                prev_prn = chans[(size_t) b0 * nchan + c].prn;      // block b0 continues whatever comes in (decided later)
+                link->prn_first[c] = prev_prn;
+                link->first_phase[c] = prev_prn > 0 ? chans[(size_t) b0 * nchan + c].carr_phase : 0.0;
+            }
             for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
                 BlockChanDev &o = ctx->h_bc[i];
                 memset(&o, 0, sizeof o);
-                for (int u = 0; u < ctx->units; u++) ctx->h_guess[((size_t) b * ctx->units + u) * nchan + c] = 0.0;
+                ctx->h_guess[i] = 0.0;
+                ctx->h_guess_abs[i] = absolute ? 1 : 0;
                 if (in.prn <= 0) {
                     prev_prn = 0;
+                    absolute = true;                        // whatever follows starts from an allocation phase
                     continue;
                 }
                 if (in.prn > 32 || in.iword < 0 || in.iword >= GPSB200_NAV_WORDS || in.ibit < 0 || in.ibit >= 30 ||
@@ -191,30 +228,37 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                     return;
                 }
                 // a slot whose satellite changed (or the first block of a call): the caller's carr_phase applies
-                if (in.prn != prev_prn) {
-                    if (!(in.carr_phase >= 0.0 && in.carr_phase < 1.0)) {
-                        status[c] = GPSB200_ERR_ARG;
-                        return;
-                    }
-                    acc = in.carr_phase;
+                if (!(in.carr_phase >= 0.0 && in.carr_phase < 1.0)) {      // read whenever a slot takes a new satellite
+                    status[c] = GPSB200_ERR_ARG;
+                    return;
                 }
+                if (in.prn != prev_prn) {
+                    acc = in.carr_phase;
+                    absolute = true;
+                }
+                ctx->h_guess_abs[i] = absolute ? 1 : 0;
                 prev_prn = in.prn;
                 o.c_carr = in.f_carr * delt;                    // gps.c:2821
                 o.c_code = in.f_code * delt;                    // gps.c:2789
                 o.gain = in.gain;
+                o.carr_in = in.carr_phase;
                 o.code0 = in.code_phase;
                 o.prn = in.prn;
                 o.nav0 = (uint32_t) in.iword | ((uint32_t) in.ibit << 8) | ((uint32_t) in.icode << 16);
                 o.frame = in.nav_frame;
-                const long double per_unit = (long double) ctx->unit_samples *
-                                             ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
-                for (int u = 0; u < ctx->units; u++) {
-                    double g = (double) acc;
-                    if (!(g >= 0.0 && g < 1.0)) g = 0.0;
-                    ctx->h_guess[((size_t) b * ctx->units + u) * nchan + c] = g;
-                    acc += per_unit;
-                    acc -= floorl(acc);
-                }
+                double g = (double) acc;
+                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                ctx->h_guess[i] = g;
+                acc += (long double) GPSB200_BLOCK_SAMPLES *
+                       ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
+                acc -= floorl(acc);
+            }
+            if (link) {
+                link->prn_last[c] = prev_prn > 0 ? prev_prn : 0;
+                link->reset_inside[c] = absolute ? 1 : 0;
+                double g = (double) acc;
+                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                link->value[c] = g;
             }
         }
     });
@@ -230,62 +274,135 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
     return GPSB200_OK;
 }
 
-// Host fix-up scan: exact start phase of every block from the probes, serial over blocks
-// per channel, parallel over channels. Returns the number of blocks that needed the
-// sequential fallback walk.
-int64_t resolve_chain(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
-                      std::vector<ChainState> &chain) {
-    std::vector<int64_t> fallbacks(nchan, 0);
+// Second pass of the relative mode: the (guessed) incoming state is known now.
+void finalize_guesses(gpsb200_ctx *ctx, int b0, int b1, int nchan, const int32_t *prn_in, const double *phase_in) {
+    ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
+        for (int c = c_lo; c < c_hi; c++) {
+            const BlockChanDev &first = ctx->h_bc[(size_t) b0 * nchan + c];
+            const bool cont = prn_in && phase_in && first.prn > 0 && prn_in[c] == first.prn;
+            const double off = cont ? phase_in[c] : first.carr_in;
+            for (int b = b0; b < b1; b++) {
+                const size_t i = (size_t) b * nchan + c;
+                if (ctx->h_guess_abs[i] || ctx->h_bc[i].prn <= 0) continue;
+                double g = ctx->h_guess[i] + off;
+                if (g >= 1.0) g -= 1.0;
+                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                ctx->h_guess[i] = g;
+            }
+        }
+    });
+}
+
+// One block of the chain, resolved on the host from its block probe (the first level of the speculation);
+// the exact sequential walk when the probe cannot be used. Returns 1 when it had to walk.
+inline int resolve_block(ChainState &st, const BlockChanDev &bc, const CarrierProbe &probe, double &start_out) {
+    if (bc.prn <= 0) {
+        st.prn = 0;
+        start_out = 0.0;
+        return 0;
+    }
+    if (st.prn != bc.prn) st.phase = bc.carr_in;
+    st.prn = bc.prn;
+    start_out = st.phase;
+    double xe;
+    if (carrier_fixup(st.phase, bc.c_carr, probe, xe)) {
+        st.phase = xe;
+        return 0;
+    }
+    int64_t dummy = 0;
+    nco_advance<NCO_CARRIER>(st.phase, bc.c_carr, GPSB200_BLOCK_SAMPLES, dummy);
+    return 1;
+}
+
+// Host scan of the two-level chain for blocks [b0, b1) (b0 is a span boundary of this launch): one
+// carrier_fixup per SPAN from the span summaries k_chain left in mapped host memory; a span the device
+// could not chain speculatively (reallocation inside it, Doppler zero crossing, a rejected block probe)
+// or whose summary does not fit the true start phase is resolved block by block from the block probes.
+// Serial over spans per channel, parallel over channels. Returns the number of blocks walked sequentially.
+int64_t resolve_chain(gpsb200_ctx *ctx, int b0, int b1, int nchan, std::vector<ChainState> &chain,
+                      int64_t *spans_regular, int64_t *spans_slow) {
+    std::vector<int64_t> fallbacks(nchan, 0), reg(nchan, 0), slow(nchan, 0);
+    const int K = kSpanBlocks;
+    const int nspan = (b1 - b0 + K - 1) / K;
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
             ChainState st = chain[c];
-            for (int b = b0; b < b1; b++) {
-                const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
-                const size_t i = (size_t) b * nchan + c;
-                for (int u = 0; u < ctx->units; u++) ctx->h_carr0[((size_t) b * ctx->units + u) * nchan + c] = 0.0;
-                if (in.prn <= 0) {
+            for (int sp = 0; sp < nspan; sp++) {
+                const int s0 = b0 + sp * K, s1 = std::min(b1, s0 + K);
+                SpanRes &res = ctx->h_span_res[(size_t) (s0 / K) * nchan + c];
+                const BlockChanDev &first = ctx->h_bc[(size_t) s0 * nchan + c];
+                bool idle = true, uniform = true;
+                for (int b = s0; b < s1; b++) {
+                    const int prn = ctx->h_bc[(size_t) b * nchan + c].prn;
+                    idle &= prn <= 0;
+                    uniform &= prn == first.prn;
+                }
+                res.start = res.shift = 0.0;
+                res.variant = 0;
+                if (idle) {
+                    res.mode = 2;
                     st.prn = 0;
                     continue;
                 }
-                if (st.prn != in.prn) st.phase = in.carr_phase;
-                st.prn = in.prn;
-                const double cc = ctx->h_bc[i].c_carr;
-                for (int u = 0; u < ctx->units; u++) {
-                    const size_t iu = ((size_t) b * ctx->units + u) * nchan + c;
-                    ctx->h_carr0[iu] = st.phase;
-                    double xe;
-                    if (carrier_fixup(st.phase, cc, ctx->h_probe[iu], xe)) {
+                if (uniform && first.prn > 0) {
+                    const double start = st.prn == first.prn ? st.phase : first.carr_in;
+                    const CarrierProbe &sum = ctx->h_span_sum[(size_t) (s0 / K) * nchan + c];
+                    double xe, d;
+                    int v;
+                    if (carrier_fixup(start, first.c_carr, sum, xe, &v, &d, 1.0)) {
+                        res.mode = 0;
+                        res.start = start;
+                        res.shift = d;
+                        res.variant = v;
+                        st.prn = first.prn;
                         st.phase = xe;
-                    } else {
-                        int64_t dummy = 0;
-                        nco_advance<NCO_CARRIER>(st.phase, cc, ctx->unit_samples, dummy);
-                        ++fallbacks[c];
+                        ++reg[c];
+                        continue;
                     }
+                }
+                // block by block (first level only)
+                res.mode = 1;
+                ++slow[c];
+                for (int b = s0; b < s1; b++) {
+                    const size_t i = (size_t) b * nchan + c;
+                    fallbacks[c] += resolve_block(st, ctx->h_bc[i], ctx->h_probe[i], ctx->h_carr0[i]);
                 }
             }
             chain[c] = st;
         }
     });
-    // fault injection for tests/test_gpu_parity.py::test_chain_self_check_catches_corruption: corrupt one
-    // resolved start phase by one ulp; the device self-check in k_checkpoints must notice
-    if (getenv("GPSB200_FAULT_INJECT_CHAIN") && b1 - b0 > 6 && ctx->h_bc[(size_t) (b0 + 5) * nchan].prn > 0 &&
-        ctx->h_bc[(size_t) (b0 + 4) * nchan].prn == ctx->h_bc[(size_t) (b0 + 5) * nchan].prn) {
-        double &v = ctx->h_carr0[(size_t) (b0 + 5) * ctx->units * nchan];
-        v = bits_f64(f64_bits(v) ^ 1ull);
+    // test hook of the device self-check (gpsb200_debug_corrupt_chain): corrupt the resolution of one span by
+    // one unit of the rounding grid; k_checkpoints must notice
+    if (ctx->fault_inject_chain && b1 - b0 > 6) {
+        SpanRes &r = ctx->h_span_res[(size_t) (b0 / K) * nchan];
+        if (r.mode == 0) r.shift += 0x1p-51;
+        else if (r.mode == 1) {
+            double &v = ctx->h_carr0[(size_t) (b0 + 5) * nchan];
+            v = bits_f64(f64_bits(v) ^ 1ull);
+        }
     }
     int64_t n = 0;
-    for (auto f : fallbacks) n += f;
+    for (int c = 0; c < nchan; c++) {
+        n += fallbacks[c];
+        if (spans_regular) *spans_regular += reg[c];
+        if (spans_slow) *spans_slow += slow[c];
+    }
     return n;
 }
 
 void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, int sample_size, void *out) {
+    // blk0 is a multiple of kSpanBlocks whenever the chain kernels are launched with these arguments
     const size_t off = (size_t) blk0 * nchan;
     a.bc = ctx->d_bc + off;
-    a.carr0 = ctx->d_carr0 + off * ctx->units;
-    a.guess = ctx->d_guess + off * ctx->units;
-    a.probe = ctx->d_probe + off * ctx->units;
-    a.units = ctx->units;
-    a.unit_samples = ctx->unit_samples;
+    a.carr0 = ctx->d_carr0 + off;
+    a.guess = ctx->d_guess + off;
+    a.probe = ctx->d_probe + off;
+    a.probe_host = ctx->d_probe_host + off;
+    a.spec = ctx->d_spec + off;
+    a.span_blocks = kSpanBlocks;
+    a.nspan = (nblk + kSpanBlocks - 1) / kSpanBlocks;
+    a.span_sum = ctx->d_span_sum + (size_t) (blk0 / kSpanBlocks) * nchan;
+    a.span_res = ctx->d_span_res + (size_t) (blk0 / kSpanBlocks) * nchan;
     a.ck = ctx->d_ck + off * ctx->nruns;
     a.nav = ctx->d_nav;
     a.chipbits = ctx->d_chips;
@@ -298,6 +415,8 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.nruns = ctx->nruns;
     a.run_samples = ctx->cfg.run_samples;
     a.iq16 = sample_size == GPSB200_SC16;
+    a.check_stride = 1;
+    a.check_phase = 0;
     // lanes per run follow the channel count; a CTA takes up to 24 warps' worth of runs
     const int grp = nchan > 16 ? 32 : (nchan > 8 ? 16 : 8);
     const int rpw = 32 / grp;
@@ -322,21 +441,134 @@ int check_call(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int ncha
         (sample_size != GPSB200_SC08 && sample_size != GPSB200_SC16))
         return fail(ctx, GPSB200_ERR_ARG, "bad arguments (nchan must equal cfg.max_chan; 1 <= nblk <= cfg.max_blocks)");
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
+    if (ctx->pending.active) return fail(ctx, GPSB200_ERR_ARG, "a call begun with gpsb200_synth_begin has not been finished");
     CU(cudaSetDevice(ctx->cfg.device));     // the caller may be a thread that never selected the context's device
     return GPSB200_OK;
 }
 
+// Wait for everything this context has in flight (error paths: the caller may free its buffers once it
+// sees the error code, so no copy into them may still be pending).
+void drain(gpsb200_ctx *ctx, cudaStream_t extra) {
+    if (extra) cudaStreamSynchronize(extra);
+    cudaStreamSynchronize(ctx->s_compute);
+    cudaStreamSynchronize(ctx->s_pre);
+    cudaStreamSynchronize(ctx->s_copy);
+}
+
+// First part of a pipeline segment [b0, b1): host records + guesses, parameters up, carrier tables.
+int segment_params(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan, int sample_size,
+                   void *dst_dev, cudaStream_t sp, const std::vector<ChainState> &chain, gpsb200_stats_t &st,
+                   SynthArgs &a, gpsb200_slice_link_t *link) {
+    const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
+    const int nb = b1 - b0;
+    const size_t off = (size_t) b0 * nchan, cnt = (size_t) nb * nchan;
+    double t0 = now_ms();
+    int rc = prepare_blocks(ctx, chans, b0, b1, nchan, chain, link);
+    if (rc) return rc;
+    st.host_chain_ms += now_ms() - t0;
+    CU(cudaMemcpyAsync(ctx->d_bc + off, ctx->h_bc + off, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, sp));
+    fill_args(ctx, a, b0, nb, nchan, sample_size, (char *) dst_dev + (size_t) b0 * blk_bytes);
+    CU(launch_tables(a, sp));                        // needs only the parameters: off the chain's critical path
+    st.launches += 1;
+    st.h2d_bytes += (int64_t) (cnt * sizeof(BlockChanDev));
+    return GPSB200_OK;
+}
+
+// Second part: everything speculative -- guesses up, block probes, span chaining. Needs no true start phase.
+int segment_probe(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, gpsb200_stats_t &st, bool first,
+                  const SynthArgs &a) {
+    const size_t off = (size_t) b0 * nchan, cnt = (size_t) (b1 - b0) * nchan;
+    CU(cudaMemcpyAsync(ctx->d_guess + off, ctx->h_guess + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+    if (first) CU(cudaEventRecord(ctx->ev[1], sp));
+    CU(launch_probe(a, sp));
+    CU(launch_chain(a, sp));
+    if (first) CU(cudaEventRecord(ctx->ev[2], sp));
+    st.launches += 2;
+    st.h2d_bytes += (int64_t) (cnt * sizeof(double));
+    st.d2h_bytes += (int64_t) (cnt * sizeof(CarrierProbe) + (size_t) a.nspan * nchan * sizeof(CarrierProbe));
+    return GPSB200_OK;
+}
+
+// Second half: wait for the span summaries, host scan from the chain state, resolutions up, exact run
+// checkpoints (+ device self-check). After it the segment's synthesis may be enqueued behind sp.
+int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, std::vector<ChainState> &chain,
+                    gpsb200_stats_t &st, bool first, const SynthArgs &a) {
+    CU(cudaStreamSynchronize(sp));                   // probes and span summaries are in (mapped) host memory now
+    const double t0 = now_ms();
+    int64_t reg = 0, slow = 0;
+    st.chain_fallbacks += (int32_t) resolve_chain(ctx, b0, b1, nchan, chain, &reg, &slow);
+    st.host_chain_ms += now_ms() - t0;
+    const size_t off = (size_t) b0 * nchan, cnt = (size_t) (b1 - b0) * nchan;
+    const size_t soff = (size_t) (b0 / kSpanBlocks) * nchan, scnt = (size_t) a.nspan * nchan;
+    if (first) CU(cudaEventRecord(ctx->ev[3], sp));
+    CU(cudaMemcpyAsync(ctx->d_span_res + soff, ctx->h_span_res + soff, scnt * sizeof(SpanRes), cudaMemcpyHostToDevice, sp));
+    st.h2d_bytes += (int64_t) (scnt * sizeof(SpanRes));
+    if (slow > 0) {                                  // rare: per-block start phases of the host-resolved spans
+        CU(cudaMemcpyAsync(ctx->d_carr0 + off, ctx->h_carr0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        st.h2d_bytes += (int64_t) (cnt * sizeof(double));
+    }
+    CU(launch_checkpoints(a, sp));
+    if (first) CU(cudaEventRecord(ctx->ev[4], sp));
+    st.launches += 1;
+    return GPSB200_OK;
+}
+
+// Synthesis of blocks [b0, b1) in chunks, each chunk's download to dst_host enqueued on s_copy behind it.
+int synth_chunks(gpsb200_ctx *ctx, int b0, int b1, int nchan, int sample_size, void *dst_dev, void *dst_host,
+                 cudaStream_t s, gpsb200_stats_t &st, int &ichunk) {
+    const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
+    // the very first chunks are short, so that the download (the long pole of this path) starts early
+    for (int c0 = b0, nc = 0; c0 < b1; c0 += nc, ichunk++) {
+        nc = kSynthChunk;
+        if (ctx->graded_chunks) nc = c0 == 0 ? 32 : (c0 == 32 ? 96 : (c0 == 128 ? 128 : kSynthChunk));
+        nc = std::min(nc, b1 - c0);
+        SynthArgs ac{};
+        char *dout = (char *) dst_dev + (size_t) c0 * blk_bytes;
+        fill_args(ctx, ac, c0, nc, nchan, sample_size, dout);
+        CU(launch_synth(ac, s));
+        st.launches += 1;
+        CU(cudaEventRecord(ctx->ev_done[ichunk], s));
+        CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[ichunk], 0));
+        CU(cudaMemcpyAsync((char *) dst_host + (size_t) c0 * blk_bytes, dout, (size_t) nc * blk_bytes,
+                           cudaMemcpyDeviceToHost, ctx->s_copy));
+        st.d2h_bytes += (int64_t) nc * (int64_t) blk_bytes;
+    }
+    return GPSB200_OK;
+}
+
+int check_chain_errors(gpsb200_ctx *ctx) {
+    if (*ctx->h_chain_errors != 0)
+        return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
+                                                  std::to_string(*ctx->h_chain_errors) + " blocks");
+    return GPSB200_OK;
+}
+
+void seed_chain(std::vector<ChainState> &chain, int nchan, const int32_t *prn_in, const double *phase_in) {
+    for (int c = 0; c < nchan; c++) {
+        chain[c].prn = (prn_in && phase_in && prn_in[c] > 0) ? prn_in[c] : 0;
+        chain[c].phase = chain[c].prn ? phase_in[c] : 0.0;
+    }
+}
+
+void export_chain(const std::vector<ChainState> &chain, int nchan, int32_t *prn_out, double *phase_out) {
+    for (int c = 0; c < nchan; c++) {
+        if (prn_out) prn_out[c] = chain[c].prn;
+        if (phase_out) phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
+    }
+}
+
 // The whole path for nblk blocks. dst_host != NULL: the call is cut into segments; the
-// carrier-chain resolution of a segment (parameters up -> probe -> probes down -> host fix-up
-// -> start phases up -> run checkpoints) runs on its own stream and therefore CONCURRENTLY
-// with the synthesis kernels (the probe/checkpoint kernels are latency bound and fit beside
+// carrier-chain resolution of a segment (parameters up -> probes -> span chaining -> host scan over the
+// span summaries -> resolutions up -> run checkpoints) runs on its own stream and therefore CONCURRENTLY
+// with the synthesis kernels (the walk kernels are latency bound and fit beside
 // k_synth's CTAs) and the download of earlier segments; results are copied to the host chunk
 // by chunk. Else one segment on the caller's stream, results stay at dst_dev.
-int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
-                 void *dst_dev, void *dst_host, cudaStream_t s, double *carr_phase_out, gpsb200_stats_t *stats) {
+int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
+                       void *dst_dev, void *dst_host, cudaStream_t s, const int32_t *prn_in, const double *phase_in,
+                       int32_t *prn_out, double *carr_phase_out, gpsb200_stats_t *stats) {
     gpsb200_stats_t st{};
-    const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
     std::vector<ChainState> chain(nchan);
+    seed_chain(chain, nchan, prn_in, phase_in);
     int seg_blocks = dst_host ? kSegFirst : nblk;
     cudaStream_t sp = dst_host ? ctx->s_pre : s;        // stream of the pre-phase
     int rc = upload_nav(ctx, sp);
@@ -346,46 +578,18 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     int ichunk = 0;
     for (int b0 = 0, b1 = 0; b0 < nblk; b0 = b1, seg_blocks = kSegBlocks) {
         b1 = std::min(nblk, b0 + seg_blocks);
-        const int nb = b1 - b0;
-        const size_t off = (size_t) b0 * nchan, cnt = (size_t) nb * nchan;
-        // 1. host pre-pass: device records + guessed start phases
-        double t0 = now_ms();
-        rc = prepare_blocks(ctx, chans, b0, b1, nchan, chain);
-        if (rc) {
-            cudaStreamSynchronize(s);
-            cudaStreamSynchronize(sp);
-            cudaStreamSynchronize(ctx->s_copy);
-            return rc;
-        }
-        st.host_chain_ms += now_ms() - t0;
-        // 2. parameters up, speculative carrier probe, probes down
-        CU(cudaMemcpyAsync(ctx->d_bc + off, ctx->h_bc + off, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, sp));
-        const size_t offu = off * ctx->units, cntu = cnt * ctx->units;
-        CU(cudaMemcpyAsync(ctx->d_guess + offu, ctx->h_guess + offu, cntu * sizeof(double), cudaMemcpyHostToDevice, sp));
         SynthArgs a{};
-        fill_args(ctx, a, b0, nb, nchan, sample_size, (char *) dst_dev + (size_t) b0 * blk_bytes);
-        CU(launch_tables(a, sp));                        // needs only the parameters: off the chain's critical path
-        if (b0 == 0) CU(cudaEventRecord(ctx->ev[1], sp));
-        CU(launch_probe(a, sp));
-        if (b0 == 0) CU(cudaEventRecord(ctx->ev[2], sp));
-        CU(cudaStreamSynchronize(sp));                   // probes are in (mapped) host memory now
-        // 3. exact block-start phases (host, serial over blocks per channel, cheap)
-        t0 = now_ms();
-        st.chain_fallbacks += (int32_t) resolve_chain(ctx, chans, b0, b1, nchan, chain);
-        st.host_chain_ms += now_ms() - t0;
-        // 4. start phases up, run checkpoints, synthesis (+ overlapped download)
-        if (b0 == 0) CU(cudaEventRecord(ctx->ev[3], sp));
-        CU(cudaMemcpyAsync(ctx->d_carr0 + offu, ctx->h_carr0 + offu, cntu * sizeof(double), cudaMemcpyHostToDevice, sp));
-        CU(launch_checkpoints(a, sp));
-        if (b0 == 0) CU(cudaEventRecord(ctx->ev[4], sp));
+        rc = segment_params(ctx, chans, b0, b1, nchan, sample_size, dst_dev, sp, chain, st, a, nullptr);
+        if (rc) return rc;
+        rc = segment_probe(ctx, b0, b1, nchan, sp, st, b0 == 0, a);
+        if (rc) return rc;
+        rc = segment_resolve(ctx, b0, b1, nchan, sp, chain, st, b0 == 0, a);
+        if (rc) return rc;
         if (sp != s) {                                   // synthesis of this segment waits for its checkpoints
             CU(cudaEventRecord(ctx->ev_done[ichunk], sp));
             CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
             ichunk++;
         }
-        st.launches += 3;
-        st.h2d_bytes += (int64_t) (cnt * sizeof(BlockChanDev) + cntu * 2 * sizeof(double));
-        st.d2h_bytes += (int64_t) (cntu * sizeof(CarrierProbe));
         if (!dst_host) {
             // self-check result of k_checkpoints: fetched BEFORE the synthesis launch in stream order, so that the
             // host can look at it without waiting for the synthesis itself
@@ -394,22 +598,8 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
             CU(launch_synth(a, s));
             st.launches += 1;
         } else {
-            // the very first chunks are short, so that the download (the long pole of this path) starts early
-            for (int c0 = b0, nc = 0; c0 < b1; c0 += nc, ichunk++) {
-                nc = kSynthChunk;
-                if (ctx->graded_chunks) nc = c0 == 0 ? 32 : (c0 == 32 ? 96 : (c0 == 128 ? 128 : kSynthChunk));
-                nc = std::min(nc, b1 - c0);
-                SynthArgs ac{};
-                char *dout = (char *) dst_dev + (size_t) c0 * blk_bytes;
-                fill_args(ctx, ac, c0, nc, nchan, sample_size, dout);
-                CU(launch_synth(ac, s));
-                st.launches += 1;
-                CU(cudaEventRecord(ctx->ev_done[ichunk], s));
-                CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[ichunk], 0));
-                CU(cudaMemcpyAsync((char *) dst_host + (size_t) c0 * blk_bytes, dout, (size_t) nc * blk_bytes,
-                                   cudaMemcpyDeviceToHost, ctx->s_copy));
-                st.d2h_bytes += (int64_t) nc * (int64_t) blk_bytes;
-            }
+            rc = synth_chunks(ctx, b0, b1, nchan, sample_size, dst_dev, dst_host, s, st, ichunk);
+            if (rc) return rc;
         }
     }
     CU(cudaEventRecord(ctx->ev[5], s));
@@ -417,8 +607,7 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     fill_args(ctx, all, 0, nblk, nchan, sample_size, dst_dev);
     ctx->last = all;
     ctx->have_last = true;
-    if (carr_phase_out)
-        for (int c = 0; c < nchan; c++) carr_phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
+    export_chain(chain, nchan, prn_out, carr_phase_out);
     // the device self-check of the carrier chain is never skipped: a wrong start phase must not produce samples silently
     if (dst_host) {
         CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
@@ -426,9 +615,8 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
     } else {
         CU(cudaEventSynchronize(ctx->ev[6]));
     }
-    if (*ctx->h_chain_errors != 0)
-        return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
-                                                  std::to_string(*ctx->h_chain_errors) + " blocks");
+    rc = check_chain_errors(ctx);
+    if (rc) return rc;
     if (dst_host) {
         CU(cudaStreamSynchronize(s));
         CU(cudaStreamSynchronize(ctx->s_copy));
@@ -451,6 +639,19 @@ int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nc
         *stats = st;
     }
     return GPSB200_OK;
+}
+
+int run_pipeline(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
+                 void *dst_dev, void *dst_host, cudaStream_t s, const int32_t *prn_in, const double *phase_in,
+                 int32_t *prn_out, double *carr_phase_out, gpsb200_stats_t *stats) {
+    const int rc = run_pipeline_inner(ctx, chans, nblk, nchan, sample_size, dst_dev, dst_host, s, prn_in, phase_in, prn_out,
+                                      carr_phase_out, stats);
+    if (rc) {                       // nothing of this call may still be in flight when the caller sees the error
+        const std::string keep = ctx->err;
+        drain(ctx, s);
+        ctx->err = keep;
+    }
+    return rc;
 }
 
 }  // namespace
@@ -519,6 +720,44 @@ int gpsb200_carrier_probe_fixup(double start, double guess, double f_carr, int64
     return ok ? 1 : 0;
 }
 
+int gpsb200_span_chain_host(const double *f_carr, int nblk, double start_true, double start_guess, double *starts_out) {
+    // Host-only model of the two-level chain for ONE span of one satellite (what k_probe + k_chain + the host scan
+    // do): block probes from closed-form guesses, span_chain() for both variants, one carrier_fixup on the summary.
+    if (!f_carr || nblk < 1 || !starts_out) return GPSB200_ERR_ARG;
+    const double delt = 1.0 / (double) GPSB200_SAMPLERATE;
+    std::vector<CarrierProbe> probes(nblk);
+    std::vector<double> cc(nblk);
+    std::vector<SpanBlockState> spec(nblk);
+    long double acc = start_guess;
+    for (int j = 0; j < nblk; j++) {
+        cc[j] = f_carr[j] * delt;
+        double g = (double) acc;
+        if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+        carrier_probe(g, cc[j], GPSB200_BLOCK_SAMPLES, probes[j]);
+        acc += (long double) GPSB200_BLOCK_SAMPLES * ((long double) cc[j] + (long double) carrier_drift_per_step(cc[j]));
+        acc -= floorl(acc);
+    }
+    CarrierProbe sum{}, part{};
+    bool ok[2];
+    for (int V = 0; V < 2; V++) {
+        span_chain(probes.data(), OneSatellite{cc.data()}, nblk, 1, start_guess, V, part, ok[V], spec.data());
+        if (V == 0) {
+            sum.x_w = part.x_w;
+            sum.n_w = part.n_w;
+        }
+        sum.x_end[V] = part.x_end[V];
+        sum.m_pos[V] = ok[V] ? part.m_pos[V] : 0.0;
+        sum.m_neg[V] = ok[V] ? part.m_neg[V] : 0.0;
+    }
+    double xe, d;
+    int v;
+    if (!carrier_fixup(start_true, cc[0], sum, xe, &v, &d, 1.0)) return 0;
+    starts_out[0] = start_true;
+    for (int j = 1; j < nblk; j++) starts_out[j] = spec[j].start[v] + d;
+    starts_out[nblk] = xe;
+    return 1;
+}
+
 int gpsb200_carrier_chain(const gpsb200_chan_t *chans, int nblk, int nchan, const double *phase_in,
                           double *phase_out, int threads) {
     if (!chans || !phase_out || nblk < 0 || nchan < 1) return GPSB200_ERR_ARG;
@@ -568,17 +807,6 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
         return GPSB200_ERR_ARG;
     }
     ctx->nruns = GPSB200_BLOCK_SAMPLES / c.run_samples;
-    // Carrier-chain units per block. 1 = whole blocks (default). Finer units (GPSB200_UNITS=5) give
-    // the latency-bound walk kernels more, shorter threads, but measured on B200 the 5x larger
-    // probe table written to mapped host memory and the 5x longer host scan cost more than they save
-    // (k_probe 3.2 -> 6.7 ms, host 3.2 -> 8.9 ms at 32 channels), so this stays an experiment knob.
-    if (const char *ev = getenv("GPSB200_UNITS")) {
-        const int u = atoi(ev);
-        if (u > 1 && GPSB200_BLOCK_SAMPLES % u == 0 && (GPSB200_BLOCK_SAMPLES / u) % c.run_samples == 0) {
-            ctx->units = u;
-            ctx->unit_samples = GPSB200_BLOCK_SAMPLES / u;
-        }
-    }
     if (const char *ev = getenv("GPSB200_GRADED_CHUNKS")) ctx->graded_chunks = atoi(ev) != 0;
     ctx->pool.reset(new WorkerPool(std::min(c.host_threads, c.max_chan)));
     *out = ctx;   // from here on errors are reported through the context
@@ -601,15 +829,24 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaMalloc(&ctx->d_atab, (size_t) c.max_blocks * kAtabRows * 32 * sizeof(int32_t)));
     CU(cudaMalloc(&ctx->d_chain_errors, sizeof(int)));
     CU(cudaHostAlloc(&ctx->h_chain_errors, sizeof(int), cudaHostAllocDefault));
-    const size_t nbu = nbc * ctx->units;
-    CU(cudaMalloc(&ctx->d_guess, nbu * sizeof(double)));
-    CU(cudaHostAlloc(&ctx->h_guess, nbu * sizeof(double), cudaHostAllocDefault));
-    CU(cudaMalloc(&ctx->d_carr0, nbu * sizeof(double)));
-    CU(cudaHostAlloc(&ctx->h_carr0, nbu * sizeof(double), cudaHostAllocDefault));
-    // probe results are written by the kernel straight into mapped pinned host memory: a
-    // copy-engine download would queue behind the large result downloads of earlier segments
-    CU(cudaHostAlloc(&ctx->h_probe, nbu * sizeof(CarrierProbe), cudaHostAllocMapped));
-    CU(cudaHostGetDevicePointer((void **) &ctx->d_probe, ctx->h_probe, 0));
+    CU(cudaMalloc(&ctx->d_guess, nbc * sizeof(double)));
+    CU(cudaHostAlloc(&ctx->h_guess, nbc * sizeof(double), cudaHostAllocDefault));
+    ctx->h_guess_abs.assign(nbc, 1);
+    CU(cudaMalloc(&ctx->d_carr0, nbc * sizeof(double)));
+    CU(cudaHostAlloc(&ctx->h_carr0, nbc * sizeof(double), cudaHostAllocDefault));
+    // block probes: one copy in HBM (k_chain reads it), one written by the kernel straight into mapped
+    // pinned host memory for the host's block-by-block fallback; span summaries only in mapped host memory
+    // (a copy-engine download would queue behind the large result downloads of earlier segments)
+    CU(cudaMalloc(&ctx->d_probe, nbc * sizeof(CarrierProbe)));
+    CU(cudaHostAlloc(&ctx->h_probe, nbc * sizeof(CarrierProbe), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **) &ctx->d_probe_host, ctx->h_probe, 0));
+    ctx->max_spans = (c.max_blocks + kSpanBlocks - 1) / kSpanBlocks + 1;
+    const size_t nsc = (size_t) ctx->max_spans * c.max_chan;
+    CU(cudaHostAlloc(&ctx->h_span_sum, nsc * sizeof(CarrierProbe), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **) &ctx->d_span_sum, ctx->h_span_sum, 0));
+    CU(cudaMalloc(&ctx->d_spec, nbc * sizeof(SpanBlockState)));
+    CU(cudaMalloc(&ctx->d_span_res, nsc * sizeof(SpanRes)));
+    CU(cudaHostAlloc(&ctx->h_span_res, nsc * sizeof(SpanRes), cudaHostAllocDefault));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
     CU(cudaMalloc(&ctx->d_nav, navb));
     CU(cudaHostAlloc(&ctx->h_nav, navb, cudaHostAllocDefault));
@@ -646,6 +883,11 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFree(ctx->d_carr0);
     cudaFreeHost(ctx->h_carr0);
     cudaFreeHost(ctx->h_probe);
+    cudaFree(ctx->d_probe);
+    cudaFreeHost(ctx->h_span_sum);
+    cudaFree(ctx->d_spec);
+    cudaFree(ctx->d_span_res);
+    cudaFreeHost(ctx->h_span_res);
     cudaFree(ctx->d_nav);
     cudaFreeHost(ctx->h_nav);
     cudaFree(ctx->d_chips);
@@ -675,13 +917,199 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
     int rc = check_call(ctx, chans, nblk, nchan, sample_size, dst_device);
     if (rc) return rc;
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
-    return run_pipeline(ctx, chans, nblk, nchan, sample_size, dst_device, nullptr, s, carr_phase_out, stats);
+    return run_pipeline(ctx, chans, nblk, nchan, sample_size, dst_device, nullptr, s, nullptr, nullptr, nullptr,
+                        carr_phase_out, stats);
+}
+
+// ---- time-slice hand-over: one call in three steps (see include/gpsb200.h) --------------------------
+int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
+                          void *dst_device, void *dst_host, void *stream_, gpsb200_slice_link_t *link) {
+    int rc = check_call(ctx, chans, nblk, nchan, sample_size, dst_device ? dst_device : dst_host);
+    if (rc) return rc;
+    if (!dst_device) {                          // host destination only: stage in the context's own device buffer
+        const size_t need = (size_t) ctx->cfg.max_blocks * GPSB200_BLOCK_ELEMS * sample_size;
+        if (ctx->out_bytes < need) {
+            cudaFree(ctx->d_out);
+            ctx->d_out = nullptr;
+            ctx->out_bytes = 0;
+            CU(cudaMalloc(&ctx->d_out, need));
+            ctx->out_bytes = need;
+        }
+        dst_device = ctx->d_out;
+    }
+    if (!link) return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_prepare: link is NULL");
+    cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
+    rc = upload_nav(ctx, s);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), s));
+    CU(cudaEventRecord(ctx->ev[0], s));
+    std::vector<ChainState> none(nchan);
+    gpsb200_stats_t st{};
+    SynthArgs a{};
+    memset(link, 0, sizeof *link);
+    rc = segment_params(ctx, chans, 0, nblk, nchan, sample_size, dst_device, s, none, st, a, link);
+    if (rc) {
+        const std::string keep = ctx->err;
+        drain(ctx, s);
+        ctx->err = keep;
+        return rc;
+    }
+    ctx->last = a;
+    ctx->have_last = false;
+    ctx->pending.active = true;
+    ctx->pending.probed = false;
+    ctx->pending.nblk = nblk;
+    ctx->pending.nchan = nchan;
+    ctx->pending.sample_size = sample_size;
+    ctx->pending.dst = dst_device;
+    ctx->pending.dst_host = dst_host;
+    ctx->pending.stream = s;
+    ctx->pending.st = st;
+    return GPSB200_OK;
+}
+
+int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in) {
+    if (!ctx) return GPSB200_ERR_ARG;
+    if (!ctx->pending.active || ctx->pending.probed)
+        return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_probe: call gpsb200_slice_prepare first");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const double t0 = now_ms();
+    finalize_guesses(ctx, 0, ctx->pending.nblk, ctx->pending.nchan, prn_in, phase_guess_in);
+    ctx->pending.st.host_chain_ms += now_ms() - t0;
+    const SynthArgs a = ctx->last;
+    int rc = segment_probe(ctx, 0, ctx->pending.nblk, ctx->pending.nchan, ctx->pending.stream, ctx->pending.st, true, a);
+    if (rc) {
+        const std::string keep = ctx->err;
+        drain(ctx, ctx->pending.stream);
+        ctx->err = keep;
+        ctx->pending.active = false;
+        return rc;
+    }
+    ctx->pending.probed = true;
+    return GPSB200_OK;
+}
+
+int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
+                         double *phase_out, gpsb200_stats_t *stats) {
+    if (!ctx) return GPSB200_ERR_ARG;
+    if (!ctx->pending.active || !ctx->pending.probed)
+        return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_finish: call gpsb200_slice_prepare and gpsb200_slice_probe first");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int nblk = ctx->pending.nblk, nchan = ctx->pending.nchan;
+    cudaStream_t s = ctx->pending.stream;
+    ctx->pending.active = false;
+    std::vector<ChainState> chain(nchan);
+    seed_chain(chain, nchan, prn_in, phase_in);
+    gpsb200_stats_t st = ctx->pending.st;
+    const SynthArgs a = ctx->last;
+    int rc = segment_resolve(ctx, 0, nblk, nchan, s, chain, st, true, a);
+    if (!rc) {
+        export_chain(chain, nchan, prn_out, phase_out);       // available BEFORE the synthesis runs: hand it on
+        cudaError_t e = cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[6], s);
+        if (e == cudaSuccess) {
+            if (ctx->pending.dst_host) {
+                int ichunk = 0;
+                rc = synth_chunks(ctx, 0, nblk, nchan, ctx->pending.sample_size, ctx->pending.dst, ctx->pending.dst_host, s, st,
+                                  ichunk);
+            } else {
+                e = launch_synth(a, s);
+                st.launches += 1;
+            }
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], s);
+        if (e != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (!rc) {
+        ctx->have_last = true;
+        if (cudaEventSynchronize(ctx->ev[6]) != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, "self-check fetch failed");
+        else rc = check_chain_errors(ctx);
+    }
+    if (rc) {
+        const std::string keep = ctx->err;
+        drain(ctx, s);
+        ctx->err = keep;
+        return rc;
+    }
+    if (stats) *stats = st;
+    return GPSB200_OK;
+}
+
+int gpsb200_slice_wait(gpsb200_ctx_t *ctx) {
+    if (!ctx || !ctx->s_compute) return GPSB200_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->pending.stream) CU(cudaStreamSynchronize(ctx->pending.stream));
+    CU(cudaStreamSynchronize(ctx->s_copy));
+    return GPSB200_OK;
+}
+
+int gpsb200_slice_link_host(const gpsb200_chan_t *chans, int nblk, int nchan, gpsb200_slice_link_t *link) {
+    // the link of a slice from its parameters alone (what gpsb200_slice_prepare also returns); no device involved
+    if (!chans || !link || nblk < 1 || nchan < 1 || nchan > GPSB200_MAX_CHAN) return GPSB200_ERR_ARG;
+    const double delt = 1.0 / (double) GPSB200_SAMPLERATE;
+    memset(link, 0, sizeof *link);
+    for (int c = 0; c < nchan; c++) {
+        long double acc = 0.0L;
+        int prev = chans[c].prn;
+        bool absolute = false;
+        link->prn_first[c] = prev;
+        link->first_phase[c] = prev > 0 ? chans[c].carr_phase : 0.0;
+        for (int b = 0; b < nblk; b++) {
+            const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
+            if (in.prn <= 0) {
+                prev = 0;
+                absolute = true;
+                continue;
+            }
+            if (in.prn != prev) {
+                acc = in.carr_phase;
+                absolute = true;
+            }
+            prev = in.prn;
+            const double cc = in.f_carr * delt;
+            acc += (long double) GPSB200_BLOCK_SAMPLES * ((long double) cc + (long double) carrier_drift_per_step(cc));
+            acc -= floorl(acc);
+        }
+        link->prn_last[c] = prev > 0 ? prev : 0;
+        link->reset_inside[c] = absolute ? 1 : 0;
+        const double g = (double) acc;
+        link->value[c] = (g >= 0.0 && g < 1.0) ? g : 0.0;
+    }
+    return GPSB200_OK;
+}
+
+int gpsb200_link_apply(const gpsb200_slice_link_t *link, int nchan, const int32_t *prn_in, const double *phase_in,
+                       int32_t *prn_out, double *phase_out) {
+    if (!link || !prn_out || !phase_out || nchan < 1 || nchan > GPSB200_MAX_CHAN) return GPSB200_ERR_ARG;
+    for (int c = 0; c < nchan; c++) {
+        if (link->prn_last[c] <= 0) {
+            prn_out[c] = 0;
+            phase_out[c] = 0.0;
+            continue;
+        }
+        double ph = link->value[c];
+        if (!link->reset_inside[c]) {
+            const bool cont = prn_in && phase_in && prn_in[c] > 0 && prn_in[c] == link->prn_first[c];
+            ph += cont ? phase_in[c] : link->first_phase[c];
+            if (ph >= 1.0) ph -= 1.0;
+        }
+        prn_out[c] = link->prn_last[c];
+        phase_out[c] = (ph >= 0.0 && ph < 1.0) ? ph : 0.0;
+    }
+    return GPSB200_OK;
+}
+
+int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on) {
+    if (!ctx) return GPSB200_ERR_ARG;
+    ctx->fault_inject_chain = on != 0;
+    return GPSB200_OK;
 }
 
 int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                                  const double *phase_in, double *phase_out) {
     if (!ctx || !chans || !phase_out || nblk < 0 || nchan != ctx->cfg.max_chan) return GPSB200_ERR_ARG;
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
+    if (ctx->pending.active) return fail(ctx, GPSB200_ERR_ARG, "a call begun with gpsb200_synth_begin has not been finished");
     CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t s = ctx->s_compute;
     std::vector<ChainState> chain(nchan);
@@ -696,14 +1124,15 @@ int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans
         const gpsb200_chan_t *cw = chans + (size_t) w0 * nchan;
         int rc = prepare_blocks(ctx, cw, 0, nw, nchan, chain);
         if (rc) return rc;
-        const size_t cnt = (size_t) nw * nchan, cntu = cnt * ctx->units;
+        const size_t cnt = (size_t) nw * nchan;
         CU(cudaMemcpyAsync(ctx->d_bc, ctx->h_bc, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(ctx->d_guess, ctx->h_guess, cntu * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_guess, ctx->h_guess, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
         SynthArgs a{};
         fill_args(ctx, a, 0, nw, nchan, GPSB200_SC08, nullptr);
         CU(launch_probe(a, s));
+        CU(launch_chain(a, s));
         CU(cudaStreamSynchronize(s));
-        resolve_chain(ctx, cw, 0, nw, nchan, chain);
+        resolve_chain(ctx, 0, nw, nchan, chain, nullptr, nullptr);
     }
     ctx->have_last = false;
     for (int c = 0; c < nchan; c++) phase_out[c] = chain[c].prn > 0 ? chain[c].phase : 0.0;
@@ -717,7 +1146,10 @@ int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream_, i
     SynthArgs a = ctx->last;
     if (dst_device) a.out = dst_device;
     if (kernel_mask & 8) CU(launch_tables(a, s));
-    if (kernel_mask & 4) CU(launch_probe(a, s));
+    if (kernel_mask & 4) {
+        CU(launch_probe(a, s));
+        CU(launch_chain(a, s));
+    }
     if (kernel_mask & 1) CU(launch_checkpoints(a, s));
     if (kernel_mask & 2) CU(launch_synth(a, s));
     return GPSB200_OK;
@@ -735,7 +1167,8 @@ int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nb
         CU(cudaMalloc(&ctx->d_out, need));
         ctx->out_bytes = need;
     }
-    return run_pipeline(ctx, chans, nblk, nchan, sample_size, ctx->d_out, dst, ctx->s_compute, carr_phase_out, stats);
+    return run_pipeline(ctx, chans, nblk, nchan, sample_size, ctx->d_out, dst, ctx->s_compute, nullptr, nullptr, nullptr,
+                        carr_phase_out, stats);
 }
 
 }  // extern "C"

@@ -371,12 +371,20 @@ GPSB_HD void carrier_probe(double guess, double c, int64_t n, CarrierProbe &o) {
 
 // Exact end-of-block carrier phase from the true start s and the probe of a guessed start.
 // Returns false when the speculation cannot be used (caller then runs nco_advance).
-GPSB_HD bool carrier_fixup(double s, double c, const CarrierProbe &p, double &x_end) {
+// v_out / d_out (optional): the parity variant chosen and the shift of the true trajectory against it;
+// `safety` scales the margins (0.5 for a block probe: half the measured room; 1.0 for a span summary whose
+// margins are already net of the safety factor and of the per-block shifts, see span_chain()).
+// pre_mp / pre_mn (optional): binade margins of the states the walk from s to the first wrap visited -- how far
+// THAT piece of trajectory could itself be shifted (span_chain() walks a speculative start here).
+GPSB_HD bool carrier_fixup(double s, double c, const CarrierProbe &p, double &x_end, int *v_out = nullptr,
+                           double *d_out = nullptr, double safety = 0.5, double *pre_mp = nullptr,
+                           double *pre_mn = nullptr) {
     if (p.n_w < 0) return false;
     double a = s;
     bool wrapped = false, ok = true;
+    if (pre_mp) *pre_mp = *pre_mn = 1.0;
     // the true trajectory must wrap for the first time exactly at step n_w
-    const int64_t done = carrier_walk(a, c, p.n_w, true, wrapped, ok, nullptr, nullptr);
+    const int64_t done = carrier_walk(a, c, p.n_w, true, wrapped, ok, pre_mp, pre_mn);
     if (!ok || !wrapped || done != p.n_w) return false;
     const double G = carrier_grid(c);
     const double d0 = a - p.x_w;                        // exact: both multiples of G, both small
@@ -387,9 +395,79 @@ GPSB_HD bool carrier_fixup(double s, double c, const CarrierProbe &p, double &x_
     const int v = (int) (qi & 1);
     const double d = d0 - (v ? G : 0.0);                // even multiple of G
     // half the measured room as a safety factor (margins are ~1e-7, shifts ~1e-12)
-    if (!(d < 0.5 * p.m_pos[v] && -d < 0.5 * p.m_neg[v])) return false;
+    if (!(d < safety * p.m_pos[v] && -d < safety * p.m_neg[v])) return false;
     x_end = p.x_end[v] + d;                             // exact: the sum IS the true state
+    if (v_out) *v_out = v;
+    if (d_out) *d_out = d;
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Second level of the parallel-in-time chain: SPANS of consecutive blocks.
+//
+// Once two trajectories of one satellite differ by an even multiple of G they stay exactly parallel ACROSS
+// block boundaries too (the increment changes, the argument of carrier_probe() does not: the shift is a
+// multiple of every rounding grid in play, ties resolve identically) -- as long as they share the binade
+// at every step and the sign of the increment (hence G) does not change. So a whole span of K blocks can be
+// resolved SPECULATIVELY on the device: span_chain() chains the K block probes from the span's guessed
+// start phase exactly like the host scan does, once per parity variant V of the first block, and records
+// the speculative start phase of every block plus how far the whole speculative trajectory may still be
+// shifted. The result is a CarrierProbe for the span as a whole: the host turns the TRUE start phase of
+// the span into the true end phase with ONE carrier_fixup() (safety 1.0) -- K times fewer serial links --
+// and the true start phase of block j is the speculative one plus the span's shift D.
+// A span is REGULAR when one satellite holds the slot in all its blocks, every increment has the same
+// sign (and is not 0), the first block wraps, and every block probe could be used; otherwise (reallocation
+// inside the span, Doppler zero crossing, a rejected probe: all rare) ok = 0 and the host resolves that
+// span block by block from the block probes.
+struct SpanBlockState {      // per (block, channel): speculative start phase of the block for V = 0, 1
+    double start[2];
+};
+
+// probes / blocks: element j of the span lives at index j * stride; param(j, c, prn) yields block j's carrier
+// increment and satellite.
+template <class ParamFn>
+GPSB_HD void span_chain(const CarrierProbe *probes, ParamFn param, int nblk_span, size_t stride, double guess, int V,
+                        CarrierProbe &sum, bool &ok, SpanBlockState *blocks) {
+    ok = false;
+    sum.n_w = -1;
+    sum.pad = 0;
+    sum.x_w = 0.0;
+    sum.x_end[V] = sum.m_pos[V] = sum.m_neg[V] = 0.0;
+    const CarrierProbe &p0 = probes[0];
+    blocks[0].start[V] = guess;
+    double c0;
+    int32_t prn0;
+    param(0, c0, prn0);
+    if (prn0 <= 0 || p0.n_w < 0 || c0 == 0.0) return;
+    const bool neg = c0 < 0.0;
+    double x = p0.x_end[V];
+    double mp = 0.5 * p0.m_pos[V], mn = 0.5 * p0.m_neg[V];
+    if (!(mp > 0.0 && mn > 0.0)) return;
+    for (int j = 1; j < nblk_span; j++) {
+        const size_t i = (size_t) j * stride;
+        blocks[i].start[V] = x;
+        double c;
+        int32_t prn;
+        param(j, c, prn);
+        if (prn != prn0 || c == 0.0 || (c < 0.0) != neg) return;
+        int v;
+        double d, xe, pmp, pmn;
+        if (!carrier_fixup(x, c, probes[i], xe, &v, &d, 0.5, &pmp, &pmn)) return;
+        // room left for a further shift D of the whole speculative trajectory: after the block's first wrap the
+        // block probe's margins net of this block's own shift d, before it the margins of the walk just done
+        const double a = 0.5 * probes[i].m_pos[v] - d, b = 0.5 * probes[i].m_neg[v] + d;
+        if (a < mp) mp = a;
+        if (b < mn) mn = b;
+        if (0.5 * pmp < mp) mp = 0.5 * pmp;
+        if (0.5 * pmn < mn) mn = 0.5 * pmn;
+        x = xe;
+    }
+    sum.n_w = p0.n_w;
+    sum.x_w = p0.x_w;
+    sum.x_end[V] = x;
+    sum.m_pos[V] = mp;
+    sum.m_neg[V] = mn;
+    ok = true;
 }
 
 // Expected rounding drift per step of the carrier recurrence (host only): while the phase
@@ -398,22 +476,19 @@ GPSB_HD bool carrier_fixup(double s, double c, const CarrierProbe &p, double &x_
 // carrier_probe(); accuracy only affects how often carrier_fixup() must fall back.
 inline double carrier_drift_per_step(double c) {
     if (c == 0.0) return 0.0;
-    const uint64_t MANT = (1ull << 52) - 1;
     const uint64_t cb = f64_bits(c) & 0x7FFFFFFFFFFFFFFFull;
     const int ec = (int) (cb >> 52);
-    if (ec == 0) return 0.0;
-    const uint64_t cm = (cb & MANT) | (1ull << 52);
+    if (ec == 0 || ec >= 1022) return 0.0;
+    const double ac = bits_f64(cb);
+    // In binade [2^e, 2^(e+1)) a step adds |c| rounded to that binade's grid, which FP64 itself yields as
+    // (2^e + |c|) - 2^e (round-half-even == the even neighbour once the mantissa is even); the binade is
+    // visited a fraction 2^e of the time.
     double tot = 0.0;
     for (int ex = ec + 1; ex <= 1022; ex++) {           // up to the binade [0.5, 1)
-        const int sh = ex - ec;
-        if (sh >= 53) break;
-        const uint64_t Cq = cm >> sh, rem = cm & ((1ull << sh) - 1), half = 1ull << (sh - 1);
-        double up = 0.0;                                 // R - Cq
-        if (rem > half || (rem == half && (Cq & 1))) up = 1.0;
-        const double frac = (double) rem / (double) (1ull << sh);
-        // weight 2^e times rho_e = (up - frac) * u_e, with e = ex - 1023, u_e = 2^(e-52)
-        const int e = ex - 1023;
-        tot += (up - frac) * bits_f64((uint64_t) (1023 + 2 * e - 52) << 52);
+        if (ex - ec >= 54) break;
+        const double lo = bits_f64((uint64_t) ex << 52);
+        const double stepd = (lo + ac) - lo;
+        tot += (stepd - ac) * lo;                       // exact difference, weight 2^e
     }
     return c > 0.0 ? tot : -tot;
 }

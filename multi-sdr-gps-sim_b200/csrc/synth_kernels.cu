@@ -85,47 +85,96 @@ __device__ __forceinline__ bool map_block_chan(const SynthArgs &a, int idx, int 
 }
 
 __global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
-    // two threads per (block, unit, channel): one per parity variant (nco_exact.h);
-    // "block" of the mapping = (block, unit) pair, so a warp is 32 consecutive units of one channel
-    SynthArgs m = a;
-    m.nblk = a.nblk * a.units;
-    const int nblk_pad = (m.nblk + 31) & ~31;
+    // two threads per (block, channel): one per parity variant (nco_exact.h); a warp is 32 consecutive
+    // blocks of one channel
+    const int nblk_pad = (a.nblk + 31) & ~31;
     const int per_v = nblk_pad * a.nchan;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = idx / per_v;
     idx -= v * per_v;
-    int bu, c;
-    if (v > 1 || !map_block_chan(m, idx, bu, c)) return;
-    const int b = bu / a.units;
-    const size_t i = (size_t) bu * a.nchan + c;
-    const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
+    int b, c;
+    if (v > 1 || !map_block_chan(a, idx, b, c)) return;
+    const size_t i = (size_t) b * a.nchan + c;
+    const BlockChanDev p = a.bc[i];
     CarrierProbe o;
     if (p.prn > 0) {
-        carrier_probe_variant(a.guess[i], p.c_carr, a.unit_samples, v, o);
+        carrier_probe_variant(a.guess[i], p.c_carr, kBlockSamples, v, o);
     } else {
         o.n_w = -1;
         o.x_w = 0.0;
         o.x_end[v] = o.m_pos[v] = o.m_neg[v] = 0.0;
     }
-    CarrierProbe *dst = a.probe + i;
-    if (v == 0) {
-        dst->x_w = o.x_w;
-        dst->n_w = o.n_w;
+    // two copies: HBM for k_chain, mapped host memory for the host's (rare) block-by-block fallback
+    CarrierProbe *dsts[2] = {a.probe + i, a.probe_host ? a.probe_host + i : nullptr};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        CarrierProbe *dst = dsts[k];
+        if (!dst) continue;
+        if (v == 0) {
+            dst->x_w = o.x_w;
+            dst->n_w = o.n_w;
+            dst->pad = 0;
+        }
+        dst->x_end[v] = o.x_end[v];
+        dst->m_pos[v] = o.m_pos[v];
+        dst->m_neg[v] = o.m_neg[v];
+    }
+}
+
+struct ColumnParams {
+    const BlockChanDev *col;
+    int nchan;
+    __device__ __forceinline__ void operator()(int j, double &cc, int32_t &prn) const {
+        const BlockChanDev &p = col[(size_t) j * nchan];
+        cc = p.c_carr;
+        prn = p.prn;
+    }
+};
+
+// One thread per (span, channel, parity variant): chain the span's block probes speculatively from the span's
+// guessed start phase (nco_exact.h: span_chain). Serial over the span's blocks, a few walk iterations each.
+__global__ void __launch_bounds__(64) k_chain(SynthArgs a) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_v = a.nspan * a.nchan;
+    const int V = idx / per_v;
+    idx -= V * per_v;
+    if (V > 1) return;
+    const int sp = idx / a.nchan, c = idx - sp * a.nchan;
+    const int b0 = sp * a.span_blocks, nb = min(a.span_blocks, a.nblk - b0);
+    const size_t i0 = (size_t) b0 * a.nchan + c;
+    CarrierProbe sum;
+    bool ok;
+    const ColumnParams col{a.bc + i0, a.nchan};   // this channel's column: block j at bc[j * nchan]
+    span_chain(a.probe + i0, col, nb, (size_t) a.nchan, a.guess[i0], V, sum, ok, a.spec + i0);
+    CarrierProbe *dst = a.span_sum + (size_t) sp * a.nchan + c;
+    if (V == 0) {
+        dst->x_w = sum.x_w;
+        dst->n_w = sum.n_w;
         dst->pad = 0;
     }
-    dst->x_end[v] = o.x_end[v];
-    dst->m_pos[v] = o.m_pos[v];
-    dst->m_neg[v] = o.m_neg[v];
+    dst->x_end[V] = sum.x_end[V];
+    dst->m_pos[V] = ok ? sum.m_pos[V] : 0.0;
+    dst->m_neg[V] = ok ? sum.m_neg[V] : 0.0;
+}
+
+// exact carrier phase at the first sample of block b of channel c, as the host scan resolved it
+__device__ __forceinline__ double resolved_start(const SynthArgs &a, int b, int c) {
+    const int sp = b / a.span_blocks;
+    const SpanRes r = a.span_res[(size_t) sp * a.nchan + c];
+    if (r.mode == 1) return a.carr0[(size_t) b * a.nchan + c];
+    if (r.mode == 2) return 0.0;
+    if (b == sp * a.span_blocks) return r.start;
+    return a.spec[(size_t) b * a.nchan + c].start[r.variant] + r.shift;     // exact: see span_chain()
 }
 
 __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
     // role 0: one thread per (block, channel) walks the code NCO (+ NAV position) through the block;
-    // role 1..: one thread per (block, unit, channel) walks the carrier through its unit
+    // role 1: one thread per (block, channel) walks the carrier through the block from its resolved start
     const int nblk_pad = (a.nblk + 31) & ~31;
     const int per_code = nblk_pad * a.nchan;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int b, c;
     if (idx < per_code) {
-        int b, c;
         if (!map_block_chan(a, idx, b, c)) return;
         const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
         RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
@@ -144,29 +193,22 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
         return;
     }
     idx -= per_code;
-    SynthArgs m = a;
-    m.nblk = a.nblk * a.units;
-    int bu, c;
-    if (!map_block_chan(m, idx, bu, c)) return;
-    const int b = bu / a.units, u = bu - b * a.units;
+    if (!map_block_chan(a, idx, b, c)) return;
     const BlockChanDev p = a.bc[(size_t) b * a.nchan + c];
-    const int runs_per_unit = a.unit_samples / a.run_samples;
-    RunCkpt *ck = a.ck + ((size_t) b * a.nruns + (size_t) u * runs_per_unit) * a.nchan + c;
-    double x = a.carr0[(size_t) bu * a.nchan + c];
-    for (int r = 0; r < runs_per_unit; r++) {
+    RunCkpt *ck = a.ck + (size_t) b * a.nruns * a.nchan + c;
+    double x = p.prn > 0 ? resolved_start(a, b, c) : 0.0;
+    for (int r = 0; r < a.nruns; r++) {
         ck[(size_t) r * a.nchan].x = x;
         if (p.prn <= 0) continue;
         int64_t dummy = 0;
         nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
     }
-    if (u == a.units - 1) {
-        if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
-        // Self-check of the parallel-in-time chain: the phase this exact walk ends on must BE the
-        // start phase the host resolved for the next block of the same satellite in this launch.
-        if (a.chain_errors && p.prn > 0 && b + 1 < a.nblk && a.bc[(size_t) (b + 1) * a.nchan + c].prn == p.prn &&
-            f64_bits(a.carr0[(size_t) (b + 1) * a.units * a.nchan + c]) != f64_bits(x))
-            atomicAdd(a.chain_errors, 1);
-    }
+    if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
+    // Self-check of the parallel-in-time chain: the phase this exact walk ends on must BE the start phase the
+    // two-level speculation resolved for the next block of the same satellite in this launch.
+    if (a.chain_errors && p.prn > 0 && b + 1 < a.nblk && a.bc[(size_t) (b + 1) * a.nchan + c].prn == p.prn &&
+        f64_bits(resolved_start(a, b + 1, c)) != f64_bits(x))
+        atomicAdd(a.chain_errors, 1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -474,18 +516,25 @@ cudaError_t launch_tables(const SynthArgs &a, cudaStream_t s) {
 }
 
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s) {
-    const int nblk_pad = (a.nblk + 31) & ~31, nbu_pad = (a.nblk * a.units + 31) & ~31;
-    const long total = (long) (nblk_pad + nbu_pad) * a.nchan;
+    const int nblk_pad = (a.nblk + 31) & ~31;
+    const long total = 2L * nblk_pad * a.nchan;
     const int threads = 128;
     k_checkpoints<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s) {
-    const int nblk_pad = (a.nblk * a.units + 31) & ~31;
+    const int nblk_pad = (a.nblk + 31) & ~31;
     const long total = 2L * nblk_pad * a.nchan;
     const int threads = 128;
     k_probe<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chain(const SynthArgs &a, cudaStream_t s) {
+    const long total = 2L * a.nspan * a.nchan;
+    const int threads = 64;
+    k_chain<<<(unsigned) ((total + threads - 1) / threads), threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,7 @@ struct BlockChanDev {
     double c_carr;     // fl(f_carr * delt)  (gps.c:2821)
     double c_code;     // fl(f_code * delt)  (gps.c:2789)
     double gain;       // gps.c:2756
-    double reserved0;  // (start phases travel in SynthArgs::carr0)
+    double carr_in;    // the caller's carr_phase: applies when the slot's satellite differs from the previous block's
     double code0;      // code phase at the first sample (computeCodePhase, gps.c:2049)
     int32_t prn;       // 0 = slot unused
     uint32_t nav0;     // iword | ibit << 8 | icode << 16 at the first sample
@@ -34,15 +34,27 @@ struct RunCkpt {
 static_assert(sizeof(RunCkpt) == 24, "RunCkpt layout");
 
 struct CarrierProbe;          // nco_exact.h
+struct SpanBlockState;        // nco_exact.h
+
+// Resolution of one span (span_blocks consecutive blocks) of one channel slot, written by the host scan.
+struct SpanRes {
+    double start;      // exact carrier phase at the first sample of the span
+    double shift;      // regular span: exact start of block j > 0 = speculative start[V] + shift
+    int32_t variant;   // V
+    int32_t mode;      // 0: regular, 1: per-block exact start phases are in SynthArgs::carr0 (host fallback), 2: idle
+};
+static_assert(sizeof(SpanRes) == 24, "SpanRes layout");
 
 struct SynthArgs {
     const BlockChanDev *bc;   // [nblk][nchan]
-    // The carrier chain is resolved in UNITS: a block is cut into `units` pieces of
-    // `unit_samples` samples (a whole number of runs) so that the latency-bound walks of
-    // k_probe / k_checkpoints get `units` times more threads that are `units` times shorter.
-    const double *carr0;      // [nblk][units][nchan] exact carrier phase at the first sample of each unit
-    const double *guess;      // [nblk][units][nchan] guessed start phases for the speculative probe
-    CarrierProbe *probe;      // [nblk][units][nchan] probe results
+    const double *carr0;      // [nblk][nchan] exact block-start phases of spans the host resolved block by block (mode 1)
+    const double *guess;      // [nblk][nchan] guessed start phases for the speculative probe
+    CarrierProbe *probe;      // [nblk][nchan] block probes (device copy, read by k_chain)
+    CarrierProbe *probe_host; // same, mapped host memory: the host's block-by-block fallback reads them
+    CarrierProbe *span_sum;   // [nspan][nchan] span summaries (mapped host memory)
+    SpanBlockState *spec;     // [nblk][nchan] speculative block-start phases per variant
+    const SpanRes *span_res;  // [nspan][nchan] the host scan's resolution of every span
+    int span_blocks, nspan;
     RunCkpt *ck;              // [nblk][nruns][nchan]
     const uint32_t *nav;      // [frames][nchan][60]
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
@@ -51,13 +63,15 @@ struct SynthArgs {
     int *chain_errors;        // self-check counter: blocks whose walked end phase != the next block's start phase
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
-    int units, unit_samples;
+    int check_stride, check_phase;   // k_checkpoints re-walks every block; the chain self-check compares all of them
 };
 
 // Gain-scaled carrier tables of every block (gps.c:2781-2782), fetched by k_synth with TMA bulk copies.
 cudaError_t launch_tables(const SynthArgs &a, cudaStream_t s);
 // Speculative carrier walk of every (block, channel) from a guessed start phase (nco_exact.h).
 cudaError_t launch_probe(const SynthArgs &a, cudaStream_t s);
+// Speculative chaining of the block probes inside every span, both parity variants (nco_exact.h: span_chain).
+cudaError_t launch_chain(const SynthArgs &a, cudaStream_t s);
 // Run-start checkpoints for every (block, channel): exact walk, O(#binade crossings).
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s);
 // The per-sample synthesis (gps.c:2767-2857): lanes = channels, warp-sum over channels.

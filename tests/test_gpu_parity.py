@@ -300,9 +300,9 @@ def test_channel_reallocation_and_gaps_vs_oracle():
         assert np.array_equal(cp, carr)
 
 
-@pytest.mark.parametrize("knob,val", [("GPSB200_UNITS", "5"), ("GPSB200_GRADED_CHUNKS", "0")])
+@pytest.mark.parametrize("knob,val", [("GPSB200_GRADED_CHUNKS", "0")])
 def test_experiment_knobs_do_not_change_the_output(knob, val, monkeypatch):
-    # the knobs of README.md only move work around (carrier-chain units per block, download chunking)
+    # the knobs of README.md only move work around (download chunking)
     ch, nav = gps.synthetic_chans(300, 32, seed=4242)
     with gps.Context(32, 300) as ctx:
         ctx.set_nav_frames(nav)
@@ -361,14 +361,15 @@ def test_single_block_call_latency_is_far_below_real_time():
     assert med < 0.05                                      # a block is 100 ms of signal
 
 
-def test_chain_self_check_catches_corruption(monkeypatch):
+def test_chain_self_check_catches_corruption():
     # defence in depth: k_checkpoints re-derives every block's end phase by an exact walk and compares it
-    # with the start phase the host resolved for the next block; a one-ulp corruption must be reported
+    # with the start phase the two-level speculation resolved for the next block; a corruption by one unit of
+    # the rounding grid (gpsb200_debug_corrupt_chain) must be reported
     ch, nav = gps.synthetic_chans(12, 32, seed=77)
     with gps.Context(32, 12) as ctx:
         ctx.set_nav_frames(nav)
         good, _ = ctx.synth_blocks(ch, 1)
-        monkeypatch.setenv("GPSB200_FAULT_INJECT_CHAIN", "1")
+        ctx.debug_corrupt_chain(True)
         with pytest.raises(gps.GpsB200Error) as e:
             ctx.synth_blocks(ch, 1)
         assert e.value.code == -5
@@ -378,7 +379,7 @@ def test_chain_self_check_catches_corruption(monkeypatch):
         with pytest.raises(gps.GpsB200Error) as e:
             ctx.synth_blocks_device(ch, 1, dev.data_ptr())
         assert e.value.code == -5
-        monkeypatch.delenv("GPSB200_FAULT_INJECT_CHAIN")
+        ctx.debug_corrupt_chain(False)
         again, _ = ctx.synth_blocks(ch, 1)
         assert np.array_equal(good, again)
 
@@ -525,3 +526,55 @@ def test_time_sliced_stream_equals_reference_stream(ranks, tmp_path):
     got = _sliced_stream_crcs(ch, nav, edges)
     bad = np.nonzero(got != g["crcs"][:, 0])[0]
     assert bad.size == 0, (edges, bad[:10])
+
+
+def _three_step_slices(ch, nav, edges, sample_size=1):
+    """The hand-over protocol of include/gpsb200.h on one device: every slice gets its own context ("rank");
+    all ranks first run gpsb200_slice_prepare (links), the links are composed into GUESSED incoming states, every
+    rank probes speculatively from its guess, and only then the exact states travel rank to rank through
+    gpsb200_slice_finish. -> (block CRCs of the concatenated stream, total sequential fallbacks)"""
+    import torch
+    nchan = ch.shape[1]
+    ctxs, outs, links = [], [], []
+    try:
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            ctx = gps.Context(nchan, hi - lo, max_nav_frames=len(nav))
+            ctx.set_nav_frames(nav)
+            dev = torch.empty((hi - lo) * gps.BLOCK_ELEMS, dtype=torch.int8 if sample_size == 1 else torch.int16,
+                              device="cuda")
+            ctxs.append(ctx)
+            outs.append(dev)
+            links.append(ctx.slice_prepare(ch[lo:hi], sample_size, dev.data_ptr()))
+        prn, ph = None, None
+        for ctx, link in zip(ctxs, links):                    # guesses: closed form only, no GPU result involved
+            ctx.slice_probe(prn, ph)
+            prn, ph = gps.link_apply(link, nchan, prn, ph)
+        prn, ph, fallbacks = None, None, 0
+        for ctx in ctxs:                                      # exact states, rank to rank
+            prn, ph, st = ctx.slice_finish(prn, ph, want_stats=True)
+            fallbacks += st.chain_fallbacks
+        torch.cuda.synchronize()
+        crcs = np.concatenate([scenario.crc_blocks(o.cpu().numpy()) for o in outs])
+        return crcs, fallbacks, (prn, ph)
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+
+
+@pytest.mark.parametrize("ranks", [2, 8])
+def test_three_step_hand_over_equals_reference_stream(ranks, tmp_path):
+    """gpsb200_slice_prepare / _probe / _finish over K "ranks" of the 310 s reallocation scenario (cuts also on the
+    blocks where a satellite rises or sets): the concatenation is the reference's stream, and the exact state after
+    the last slice equals the one-call result."""
+    g = scenario.load_golden("sky32_lat60_310s_i8")
+    ch, nav = gps.scenario(_nav_file(tmp_path, 32), 60.0, 140.0, 0.0, seconds=310, max_chan=32, start=(2024, 1, 7, 2, 0, 0.0))
+    occ = ch["prn"]
+    change = [b for b in range(1, ch.shape[0]) if np.any(occ[b] != occ[b - 1])]
+    edges = sorted(set([gps.sharding.slice_bounds(ch.shape[0], ranks, r)[0] for r in range(ranks)] + change + [ch.shape[0]]))
+    got, fallbacks, (prn, ph) = _three_step_slices(ch, nav, edges)
+    bad = np.nonzero(got != g["crcs"][:, 0])[0]
+    assert bad.size == 0, (edges, bad[:10])
+    assert fallbacks < 0.01 * ch.size
+    want = gps.carrier_chain(ch, threads=8)
+    assert np.array_equal(ph, want)
+    assert np.array_equal(prn, np.where(occ[-1] > 0, occ[-1], 0))

@@ -230,3 +230,31 @@ def test_fifo_push_reproduces_hackrf_buffer_cadence():
     sizes = [g.size for g in got]
     assert sizes[:-1] == [262144] * 6 and sizes[-1] == 1800000 - 6 * 262144
     assert np.array_equal(np.concatenate(got), data)
+
+
+def test_span_level_chain_is_exact_or_rejected():
+    """Second level of the parallel-in-time carrier chain (nco_exact.h: span_chain): K block probes chained
+    speculatively from a GUESSED span start, then ONE fix-up with the true start. Whenever the speculation is
+    accepted, every block start and the end phase equal the sequential exact chain bit for bit."""
+    rng = np.random.default_rng(20240924)
+    accepted = 0
+    for case in range(160):
+        K = int(rng.choice([2, 5, 32, 64]))
+        f0 = rng.uniform(-6000, 6000) if rng.random() > 0.15 else rng.uniform(-400, 400)
+        f = f0 + np.cumsum(rng.uniform(-0.1, 0.1, K))
+        s = rng.uniform(0, 1)
+        g = s + rng.choice([0.0, 1e-13, -1e-12, 3e-11, -2e-10, 1e-9, 1e-6])
+        g = min(max(g, 0.0), np.nextafter(1.0, 0))
+        out = gps.span_chain_host(f, s, g)
+        if out is None:
+            continue
+        accepted += 1
+        x, want = s, [s]
+        for j in range(K):
+            x = gps.carrier_advance(x, f[j], 300000)
+            want.append(x)
+        assert np.array_equal(out, np.array(want)), (case, K, f0)
+    assert accepted > 100
+    # a Doppler zero crossing inside the span changes the rounding grid: never accepted
+    f = np.linspace(3.0, -3.0, 8) * 200.0
+    assert gps.span_chain_host(f, 0.3, 0.3) is None
