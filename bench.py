@@ -404,7 +404,7 @@ def main():
     # ---- value: the whole path, parameters in host memory (6 MB), result left in HBM ---------------------
     note("value leg: first full pass")
     st, _ = one_step(out_dev.data_ptr())
-    torch.cuda.synchronize()
+    ctx.slice_wait()
     sampler = None
     if rank == 0:
         uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
@@ -412,7 +412,7 @@ def main():
     note("value leg: %d warm-up + %d timed steps" % (args.warmup, args.steps))
     for _ in range(args.warmup):
         one_step(out_dev.data_ptr())
-        torch.cuda.synchronize()
+        ctx.slice_wait()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"k_probe_chain_ms": 0.0, "k_checkpoints_ms": 0.0, "k_synth_ms": 0.0, "host_chain_ms": 0.0}
@@ -421,7 +421,7 @@ def main():
     ev0.record(stream)
     for i in range(args.steps):
         st, ph_last = one_step(out_dev.data_ptr())
-        stream.synchronize()                                  # the output buffer is reused by the next step
+        ctx.slice_wait()                                      # completion + self-check verdict; the buffers are reused
         kern["host_chain_ms"] += st.host_chain_ms
         fallbacks += st.chain_fallbacks
     ev1.record(stream)

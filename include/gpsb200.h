@@ -140,10 +140,13 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
  *   2. gpsb200_slice_probe    incoming state as GUESSED (NULL: the slice starts the stream): speculative block
  *                             probes + span chaining are enqueued.
  *   3. gpsb200_slice_finish   incoming state EXACT (prn_in/phase_in, from the previous rank's *_out; NULL: the
- *                             stream starts here): host scan over the span summaries, run checkpoints with the
- *                             device self-check, synthesis enqueued on the stream. prn_out/phase_out (exact state
- *                             after the slice) are valid on return -- BEFORE the synthesis has run -- and are what
- *                             the next rank's gpsb200_slice_finish takes.
+ *                             stream starts here): segment by segment, as soon as a segment's probes are done, the
+ *                             host scan over its span summaries, its run checkpoints (with the device self-check) and
+ *                             its synthesis are enqueued -- the synthesis of early segments overlaps the probes of
+ *                             later ones. prn_out/phase_out (exact state after the slice) are valid on return --
+ *                             BEFORE the synthesis has run -- and are what the next rank's gpsb200_slice_finish takes.
+ *   4. gpsb200_slice_wait     blocks until the slice is complete and returns the verdict of the device self-check
+ *                             (GPSB200_ERR_INTERNAL: the output must not be used).
  * A slot continues the incoming phase only when it still holds the same satellite (prn_in[c] == prn of its first
  * block, > 0); otherwise its first block takes carr_phase from chans, exactly as between the blocks of one call.
  * chans must stay valid until gpsb200_slice_prepare returns. gpsb200_synth_blocks_device == the three steps with
@@ -157,7 +160,7 @@ typedef struct gpsb200_slice_link {
 } gpsb200_slice_link_t;
 /* dst_device and/or dst_host: with dst_host != NULL the synthesis is launched in chunks whose downloads into dst_host
  * (pinned memory) overlap later chunks, dst_device may then be NULL (a context-owned staging buffer is used);
- * gpsb200_slice_wait blocks until synthesis and downloads of the slice are complete. */
+ * gpsb200_slice_wait blocks until synthesis and downloads of the slice are complete and reports the self-check. */
 int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
                           void *dst_device, void *dst_host, void *stream, gpsb200_slice_link_t *link);
 int gpsb200_slice_wait(gpsb200_ctx_t *ctx);
@@ -245,7 +248,11 @@ int gpsb200_scenario_nav_frames(const gpsb200_scenario_t *s);
 const gpsb200_chan_t *gpsb200_scenario_chans(const gpsb200_scenario_t *s);   /* [blocks][channels] */
 const uint32_t *gpsb200_scenario_nav(const gpsb200_scenario_t *s);           /* [frames][channels][60] */
 
-/* ---- FIFO / sink boundary: the reference's own API (fifo.h:19-62) -------------- */
+/* ---- FIFO / sink boundary: the reference's own API (fifo.h:19-62) --------------
+ * Guarded by the reference header's own include guard (fifo.h:13-14), so that a translation unit of the reference
+ * that includes both headers -- in either order -- sees the declarations once (they are identical). */
+#ifndef FIFO_H
+#define FIFO_H
 struct iq_buf {
     signed char *data8;        /* 8 bit IQ data  */
     signed short *data16;      /* 16 bit IQ data */
@@ -262,6 +269,7 @@ struct iq_buf *fifo_acquire(void);
 void fifo_enqueue(struct iq_buf *buf);
 struct iq_buf *fifo_dequeue(void);
 void fifo_release(struct iq_buf *buf);
+#endif /* FIFO_H */
 /* gpsb200 extension: reproduce the stock reference's loss of buffers 1..6 of a run
  * (tail bug, fifo.c:163-168) so that iqdata.bin is byte-identical to the stock program. */
 void fifo_set_compat_drop(bool on);

@@ -118,7 +118,7 @@ private:
 struct gpsb200_ctx {
     gpsb200_config_t cfg{};
     int nruns = 0;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr, s_ck = nullptr;
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> ev_done;      // one per synthesis chunk
     BlockChanDev *d_bc = nullptr, *h_bc = nullptr;
@@ -136,7 +136,10 @@ struct gpsb200_ctx {
     CarrierProbe *h_span_sum = nullptr, *d_span_sum = nullptr;  // span summaries, mapped host memory
     SpanBlockState *d_spec = nullptr;                  // speculative block-start phases
     SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
-    int max_spans = 0;
+    int max_spans = 0, max_segs = 0;
+    double *h_seg_end = nullptr;           // pinned: device-walked end phases of every pipeline segment's last block
+    std::vector<double> seg_expect;        // what the chain says they must be
+    std::vector<cudaEvent_t> ev_seg;       // slice path: probes of segment i complete
     bool fault_inject_chain = false;       // gpsb200_debug_corrupt_chain(): test hook of the device self-check
     // state of a begun, not yet finished call (gpsb200_synth_begin / _finish)
     struct Pending {
@@ -144,7 +147,8 @@ struct gpsb200_ctx {
         int nblk = 0, nchan = 0, sample_size = 0;
         void *dst = nullptr, *dst_host = nullptr;
         cudaStream_t stream = nullptr;
-        bool probed = false;
+        bool probed = false, finished = false;
+        int nseg = 0;
         gpsb200_stats_t st{};
     } pending;
     void *d_out = nullptr;
@@ -452,6 +456,7 @@ void drain(gpsb200_ctx *ctx, cudaStream_t extra) {
     if (extra) cudaStreamSynchronize(extra);
     cudaStreamSynchronize(ctx->s_compute);
     cudaStreamSynchronize(ctx->s_pre);
+    if (ctx->s_ck) cudaStreamSynchronize(ctx->s_ck);
     cudaStreamSynchronize(ctx->s_copy);
 }
 
@@ -492,8 +497,11 @@ int segment_probe(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, 
 // Second half: wait for the span summaries, host scan from the chain state, resolutions up, exact run
 // checkpoints (+ device self-check). After it the segment's synthesis may be enqueued behind sp.
 int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, std::vector<ChainState> &chain,
-                    gpsb200_stats_t &st, bool first, const SynthArgs &a) {
-    CU(cudaStreamSynchronize(sp));                   // probes and span summaries are in (mapped) host memory now
+                    gpsb200_stats_t &st, bool first, const SynthArgs &a, cudaEvent_t probes_done = nullptr) {
+    // probes and span summaries must be in (mapped) host memory: wait for the segment's own probe event when the
+    // post-scan work runs on a stream of its own (slice path), else for the pre-phase stream
+    if (probes_done) CU(cudaEventSynchronize(probes_done));
+    else CU(cudaStreamSynchronize(sp));
     const double t0 = now_ms();
     int64_t reg = 0, slow = 0;
     st.chain_fallbacks += (int32_t) resolve_chain(ctx, b0, b1, nchan, chain, &reg, &slow);
@@ -536,13 +544,6 @@ int synth_chunks(gpsb200_ctx *ctx, int b0, int b1, int nchan, int sample_size, v
     return GPSB200_OK;
 }
 
-int check_chain_errors(gpsb200_ctx *ctx) {
-    if (*ctx->h_chain_errors != 0)
-        return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " +
-                                                  std::to_string(*ctx->h_chain_errors) + " blocks");
-    return GPSB200_OK;
-}
-
 void seed_chain(std::vector<ChainState> &chain, int nchan, const int32_t *prn_in, const double *phase_in) {
     for (int c = 0; c < nchan; c++) {
         chain[c].prn = (prn_in && phase_in && prn_in[c] > 0) ? prn_in[c] : 0;
@@ -557,27 +558,69 @@ void export_chain(const std::vector<ChainState> &chain, int nchan, int32_t *prn_
     }
 }
 
-// The whole path for nblk blocks. dst_host != NULL: the call is cut into segments; the
-// carrier-chain resolution of a segment (parameters up -> probes -> span chaining -> host scan over the
-// span summaries -> resolutions up -> run checkpoints) runs on its own stream and therefore CONCURRENTLY
-// with the synthesis kernels (the walk kernels are latency bound and fit beside
-// k_synth's CTAs) and the download of earlier segments; results are copied to the host chunk
-// by chunk. Else one segment on the caller's stream, results stay at dst_dev.
+// Pipeline segments of a call: a short first one (its chain resolution is the lead-in of everything), then long ones.
+std::vector<std::pair<int, int>> segments_of(int nblk) {
+    std::vector<std::pair<int, int>> v;
+    int len = kSegFirst;
+    for (int b0 = 0; b0 < nblk; len = kSegBlocks) {
+        const int b1 = std::min(nblk, b0 + len);
+        v.emplace_back(b0, b1);
+        b0 = b1;
+    }
+    return v;
+}
+
+// After the checkpoint kernel of segment i: remember what the chain expects at the segment's end and fetch what the
+// device's exact walk of the segment's last block ended on (k_checkpoints -> carr_end); compared in verify_chain().
+// This extends the device self-check across pipeline-segment (and call) boundaries.
+int note_segment_end(gpsb200_ctx *ctx, int iseg, int b1, int nchan, cudaStream_t sp, const std::vector<ChainState> &chain) {
+    if (iseg >= ctx->max_segs) return GPSB200_OK;
+    for (int c = 0; c < nchan; c++) {
+        const bool live = chain[c].prn > 0 && ctx->h_bc[(size_t) (b1 - 1) * nchan + c].prn == chain[c].prn;
+        ctx->seg_expect[(size_t) iseg * nchan + c] = live ? chain[c].phase : -1.0;       // -1: nothing to compare
+    }
+    CU(cudaMemcpyAsync(ctx->h_seg_end + (size_t) iseg * nchan, ctx->d_carr_end + (size_t) (b1 - 1) * nchan,
+                       (size_t) nchan * sizeof(double), cudaMemcpyDeviceToHost, sp));
+    return GPSB200_OK;
+}
+
+// Verdict of the device self-check (all of sp's work must be complete): the per-block comparisons inside the
+// checkpoint launches plus the segment-boundary comparisons.
+int verify_chain(gpsb200_ctx *ctx, int nseg, int nchan) {
+    int bad = *ctx->h_chain_errors;
+    for (int i = 0; i < std::min(nseg, ctx->max_segs); i++)
+        for (int c = 0; c < nchan; c++) {
+            const double want = ctx->seg_expect[(size_t) i * nchan + c];
+            if (want >= 0.0 && f64_bits(want) != f64_bits(ctx->h_seg_end[(size_t) i * nchan + c])) ++bad;
+        }
+    if (bad != 0)
+        return fail(ctx, GPSB200_ERR_INTERNAL, "carrier chain self-check failed on " + std::to_string(bad) + " blocks");
+    return GPSB200_OK;
+}
+
+// The whole path for nblk blocks, as a pipeline of segments: the carrier-chain resolution of a segment (parameters
+// up -> block probes -> span chaining -> host scan over the span summaries -> resolutions up -> run checkpoints)
+// runs on the context's high-priority pre-phase stream and therefore CONCURRENTLY with the synthesis kernels of
+// earlier segments on the caller's stream (the walk kernels are latency bound and fit beside k_synth's CTAs) and,
+// with a host destination, with the downloads of finished chunks. Only the first (short) segment's resolution is
+// a lead-in. dst_host == NULL: results stay at dst_dev and the call returns once everything is enqueued and the
+// chain self-check has been read.
 int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
                        void *dst_dev, void *dst_host, cudaStream_t s, const int32_t *prn_in, const double *phase_in,
                        int32_t *prn_out, double *carr_phase_out, gpsb200_stats_t *stats) {
     gpsb200_stats_t st{};
     std::vector<ChainState> chain(nchan);
     seed_chain(chain, nchan, prn_in, phase_in);
-    int seg_blocks = dst_host ? kSegFirst : nblk;
-    cudaStream_t sp = dst_host ? ctx->s_pre : s;        // stream of the pre-phase
+    cudaStream_t sp = ctx->s_pre;                       // stream of the pre-phase
+    CU(cudaEventRecord(ctx->ev[0], s));
+    CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
     int rc = upload_nav(ctx, sp);
     if (rc) return rc;
     CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), sp));
-    CU(cudaEventRecord(ctx->ev[0], s));
-    int ichunk = 0;
-    for (int b0 = 0, b1 = 0; b0 < nblk; b0 = b1, seg_blocks = kSegBlocks) {
-        b1 = std::min(nblk, b0 + seg_blocks);
+    int ichunk = 0, iseg = 0;
+    const auto segs = segments_of(nblk);
+    for (const auto &sg : segs) {
+        const int b0 = sg.first, b1 = sg.second;
         SynthArgs a{};
         rc = segment_params(ctx, chans, b0, b1, nchan, sample_size, dst_dev, sp, chain, st, a, nullptr);
         if (rc) return rc;
@@ -585,16 +628,12 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
         if (rc) return rc;
         rc = segment_resolve(ctx, b0, b1, nchan, sp, chain, st, b0 == 0, a);
         if (rc) return rc;
-        if (sp != s) {                                   // synthesis of this segment waits for its checkpoints
-            CU(cudaEventRecord(ctx->ev_done[ichunk], sp));
-            CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
-            ichunk++;
-        }
+        rc = note_segment_end(ctx, iseg++, b1, nchan, sp, chain);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_done[ichunk], sp));   // synthesis of this segment waits for its checkpoints
+        CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
+        ichunk++;
         if (!dst_host) {
-            // self-check result of k_checkpoints: fetched BEFORE the synthesis launch in stream order, so that the
-            // host can look at it without waiting for the synthesis itself
-            CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CU(cudaEventRecord(ctx->ev[6], s));
             CU(launch_synth(a, s));
             st.launches += 1;
         } else {
@@ -609,33 +648,25 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     ctx->have_last = true;
     export_chain(chain, nchan, prn_out, carr_phase_out);
     // the device self-check of the carrier chain is never skipped: a wrong start phase must not produce samples silently
-    if (dst_host) {
-        CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
-        CU(cudaStreamSynchronize(sp));
-    } else {
-        CU(cudaEventSynchronize(ctx->ev[6]));
-    }
-    rc = check_chain_errors(ctx);
+    CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
+    CU(cudaStreamSynchronize(sp));
+    rc = verify_chain(ctx, iseg, nchan);
     if (rc) return rc;
     if (dst_host) {
         CU(cudaStreamSynchronize(s));
         CU(cudaStreamSynchronize(ctx->s_copy));
     }
     if (stats) {
-        CU(cudaEventSynchronize(ctx->ev[5]));
         float ms = 0;
-        // per-kernel times of the FIRST segment (the only one when dst_host == NULL) ...
+        // per-kernel times of the FIRST segment ...
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
         st.probe_kernel_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
         st.checkpoint_kernel_ms = ms;
-        if (!dst_host) {
-            cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
-            st.synth_kernel_ms = ms;
+        if (dst_host) {      // ... and the whole span of the call's stream (a device-destination call is still running)
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
+            st.kernel_ms = ms;
         }
-        // ... and the whole span of the call's stream
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
-        st.kernel_ms = ms;
         *stats = st;
     }
     return GPSB200_OK;
@@ -816,11 +847,21 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaSetDevice(c.device));
     CU(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->s_pre, cudaStreamNonBlocking));
+    {   // the pre-phase (latency-bound walk kernels, the lead-in of everything) outranks the synthesis
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&ctx->s_pre, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->s_ck, cudaStreamNonBlocking, hi));
+    }
     for (auto &e : ctx->ev) CU(cudaEventCreate(&e));
     const int nchunk = (c.max_blocks + kSynthChunk - 1) / kSynthChunk + (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 5;
     ctx->ev_done.resize(nchunk);
     for (auto &e : ctx->ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->max_segs = (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 2;
+    ctx->ev_seg.resize(ctx->max_segs);
+    for (auto &e : ctx->ev_seg) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaHostAlloc(&ctx->h_seg_end, (size_t) ctx->max_segs * c.max_chan * sizeof(double), cudaHostAllocDefault));
+    ctx->seg_expect.assign((size_t) ctx->max_segs * c.max_chan, -1.0);
     const size_t nbc = (size_t) c.max_blocks * c.max_chan;
     CU(cudaMalloc(&ctx->d_bc, nbc * sizeof(BlockChanDev)));
     CU(cudaHostAlloc(&ctx->h_bc, nbc * sizeof(BlockChanDev), cudaHostAllocDefault));
@@ -871,6 +912,7 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     if (ctx->s_pre) cudaStreamSynchronize(ctx->s_pre);
+    if (ctx->s_ck) cudaStreamSynchronize(ctx->s_ck);
     cudaFree(ctx->d_bc);
     cudaFreeHost(ctx->h_bc);
     cudaFree(ctx->d_ck);
@@ -896,9 +938,13 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_done)
         if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_seg)
+        if (e) cudaEventDestroy(e);
+    cudaFreeHost(ctx->h_seg_end);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_pre) cudaStreamDestroy(ctx->s_pre);
+    if (ctx->s_ck) cudaStreamDestroy(ctx->s_ck);
     delete ctx;
 }
 
@@ -939,15 +985,18 @@ int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int n
     }
     if (!link) return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_prepare: link is NULL");
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
-    rc = upload_nav(ctx, s);
-    if (rc) return rc;
-    CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), s));
+    cudaStream_t sp = ctx->s_pre;
     CU(cudaEventRecord(ctx->ev[0], s));
+    CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
+    CU(cudaStreamWaitEvent(ctx->s_ck, ctx->ev[0], 0));
+    rc = upload_nav(ctx, sp);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), sp));
     std::vector<ChainState> none(nchan);
     gpsb200_stats_t st{};
     SynthArgs a{};
     memset(link, 0, sizeof *link);
-    rc = segment_params(ctx, chans, 0, nblk, nchan, sample_size, dst_device, s, none, st, a, link);
+    rc = segment_params(ctx, chans, 0, nblk, nchan, sample_size, dst_device, sp, none, st, a, link);
     if (rc) {
         const std::string keep = ctx->err;
         drain(ctx, s);
@@ -958,6 +1007,7 @@ int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int n
     ctx->have_last = false;
     ctx->pending.active = true;
     ctx->pending.probed = false;
+    ctx->pending.finished = false;
     ctx->pending.nblk = nblk;
     ctx->pending.nchan = nchan;
     ctx->pending.sample_size = sample_size;
@@ -973,11 +1023,21 @@ int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double 
     if (!ctx->pending.active || ctx->pending.probed)
         return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_probe: call gpsb200_slice_prepare first");
     CU(cudaSetDevice(ctx->cfg.device));
+    const int nblk = ctx->pending.nblk, nchan = ctx->pending.nchan;
     const double t0 = now_ms();
-    finalize_guesses(ctx, 0, ctx->pending.nblk, ctx->pending.nchan, prn_in, phase_guess_in);
+    finalize_guesses(ctx, 0, nblk, nchan, prn_in, phase_guess_in);
     ctx->pending.st.host_chain_ms += now_ms() - t0;
-    const SynthArgs a = ctx->last;
-    int rc = segment_probe(ctx, 0, ctx->pending.nblk, ctx->pending.nchan, ctx->pending.stream, ctx->pending.st, true, a);
+    int rc = GPSB200_OK, iseg = 0;
+    for (const auto &sg : segments_of(nblk)) {          // speculative work of every segment, in stream order
+        SynthArgs a{};
+        fill_args(ctx, a, sg.first, sg.second - sg.first, nchan, ctx->pending.sample_size, nullptr);
+        rc = segment_probe(ctx, sg.first, sg.second, nchan, ctx->s_pre, ctx->pending.st, sg.first == 0, a);
+        if (rc) break;
+        if (cudaEventRecord(ctx->ev_seg[iseg++], ctx->s_pre) != cudaSuccess) {
+            rc = fail(ctx, GPSB200_ERR_CUDA, "cudaEventRecord");
+            break;
+        }
+    }
     if (rc) {
         const std::string keep = ctx->err;
         drain(ctx, ctx->pending.stream);
@@ -989,6 +1049,40 @@ int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double 
     return GPSB200_OK;
 }
 
+namespace {
+int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200_stats_t &st) {
+    const int nblk = ctx->pending.nblk, nchan = ctx->pending.nchan, sample_size = ctx->pending.sample_size;
+    const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
+    cudaStream_t s = ctx->pending.stream, sk = ctx->s_ck;
+    int iseg = 0, ichunk = 0;
+    for (const auto &sg : segments_of(nblk)) {
+        const int b0 = sg.first, b1 = sg.second;
+        SynthArgs a{};
+        fill_args(ctx, a, b0, b1 - b0, nchan, sample_size, (char *) ctx->pending.dst + (size_t) b0 * blk_bytes);
+        // host scan of this segment as soon as ITS probes are done; checkpoints on a stream of their own, so that
+        // they do not queue behind the probes of later segments; the synthesis follows on the caller's stream
+        int rc = segment_resolve(ctx, b0, b1, nchan, sk, chain, st, b0 == 0, a, ctx->ev_seg[iseg]);
+        if (rc) return rc;
+        rc = note_segment_end(ctx, iseg++, b1, nchan, sk, chain);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_done[ichunk], sk));
+        CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
+        ichunk++;
+        if (ctx->pending.dst_host) {
+            rc = synth_chunks(ctx, b0, b1, nchan, sample_size, ctx->pending.dst, ctx->pending.dst_host, s, st, ichunk);
+            if (rc) return rc;
+        } else {
+            CU(launch_synth(a, s));
+            st.launches += 1;
+        }
+    }
+    ctx->pending.nseg = iseg;
+    CU(cudaEventRecord(ctx->ev[5], s));
+    CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sk));
+    return GPSB200_OK;
+}
+}  // namespace
+
 int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
                          double *phase_out, gpsb200_stats_t *stats) {
     if (!ctx) return GPSB200_ERR_ARG;
@@ -996,41 +1090,23 @@ int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double
         return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_finish: call gpsb200_slice_prepare and gpsb200_slice_probe first");
     CU(cudaSetDevice(ctx->cfg.device));
     const int nblk = ctx->pending.nblk, nchan = ctx->pending.nchan;
-    cudaStream_t s = ctx->pending.stream;
     ctx->pending.active = false;
     std::vector<ChainState> chain(nchan);
     seed_chain(chain, nchan, prn_in, phase_in);
     gpsb200_stats_t st = ctx->pending.st;
-    const SynthArgs a = ctx->last;
-    int rc = segment_resolve(ctx, 0, nblk, nchan, s, chain, st, true, a);
-    if (!rc) {
-        export_chain(chain, nchan, prn_out, phase_out);       // available BEFORE the synthesis runs: hand it on
-        cudaError_t e = cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[6], s);
-        if (e == cudaSuccess) {
-            if (ctx->pending.dst_host) {
-                int ichunk = 0;
-                rc = synth_chunks(ctx, 0, nblk, nchan, ctx->pending.sample_size, ctx->pending.dst, ctx->pending.dst_host, s, st,
-                                  ichunk);
-            } else {
-                e = launch_synth(a, s);
-                st.launches += 1;
-            }
-        }
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5], s);
-        if (e != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, cudaGetErrorString(e));
-    }
-    if (!rc) {
-        ctx->have_last = true;
-        if (cudaEventSynchronize(ctx->ev[6]) != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, "self-check fetch failed");
-        else rc = check_chain_errors(ctx);
-    }
+    const int rc = slice_finish_inner(ctx, chain, st);
     if (rc) {
         const std::string keep = ctx->err;
-        drain(ctx, s);
+        drain(ctx, ctx->pending.stream);
         ctx->err = keep;
         return rc;
     }
+    SynthArgs all{};
+    fill_args(ctx, all, 0, nblk, nchan, ctx->pending.sample_size, ctx->pending.dst);
+    ctx->last = all;
+    ctx->have_last = true;
+    ctx->pending.finished = true;
+    export_chain(chain, nchan, prn_out, phase_out);       // exact; the synthesis is still running: hand it on now
     if (stats) *stats = st;
     return GPSB200_OK;
 }
@@ -1038,8 +1114,14 @@ int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double
 int gpsb200_slice_wait(gpsb200_ctx_t *ctx) {
     if (!ctx || !ctx->s_compute) return GPSB200_ERR_ARG;
     CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->s_pre));
+    CU(cudaStreamSynchronize(ctx->s_ck));
     if (ctx->pending.stream) CU(cudaStreamSynchronize(ctx->pending.stream));
     CU(cudaStreamSynchronize(ctx->s_copy));
+    if (ctx->pending.finished) {
+        ctx->pending.finished = false;
+        return verify_chain(ctx, ctx->pending.nseg, ctx->pending.nchan);
+    }
     return GPSB200_OK;
 }
 

@@ -28,3 +28,26 @@ def test_stock_iqfile_is_enqueue_stream_minus_blocks_1_to_6(tmp_path):
     blocks = s.reshape(len(keep), 600000)
     for row, b in zip(blocks, keep):
         assert zlib.crc32(row.tobytes()) == g["crcs"][b, 0], b
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("bits", [8, 16])
+def test_reference_sink_code_runs_unmodified_on_our_fifo(bits, tmp_path):
+    """Drop-in claim of INTEGRATION.md section 3, compiled and run: the reference's own sdr.c (dispatch table,
+    sdr.c:35-87) and sdr_iqfile.c (writer thread, sdr_iqfile.c:22-77) are built unmodified and linked with
+    libgpsb200.so INSTEAD OF fifo.o (oracle/Makefile: ref_sinkfeed). A producer replays a stream through
+    fifo_acquire / fifo_enqueue exactly as gps_thread_ep does; the sink's iqdata.bin must be that stream --
+    all of it (the stock fifo.c would lose buffers 1..6, fifo.c:163-168)."""
+    exe = os.path.join(scenario.ROOT, "oracle", "_ref", "ref_sinkfeed")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(scenario.ROOT, "oracle")])
+    rng = np.random.default_rng(bits)
+    dt = np.int8 if bits == 8 else np.int16
+    info = np.iinfo(dt)
+    stream = rng.integers(info.min, info.max + 1, size=23 * 600000, dtype=dt)
+    src = tmp_path / "in.bin"
+    stream.tofile(src)
+    out = subprocess.run([exe, str(src), str(bits)], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-400:]
+    got = np.fromfile(tmp_path / "iqdata.bin", dtype=dt)
+    assert got.size == stream.size and np.array_equal(got, stream)

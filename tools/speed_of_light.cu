@@ -280,6 +280,98 @@ float run_lanes(uint32_t *out, const int32_t *tab, int nblk, int nchan, int reps
     return ms / reps;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// sol_half_table: k_synth's quiet path with the HALF carrier table (rows k and k + 256 are negatives, so
+// 256 rows = 32.8 KB suffice) -- the sign (chip x data bit x table half) is applied to the looked-up value
+// instead of being folded into the row index. Buys a third resident CTA per SM (63 instead of 42 warps),
+// costs instructions per channel-sample: the question is which effect wins on an issue-bound kernel.
+struct SmemHalf {
+    int32_t atab[256][32];
+    alignas(16) int32_t stage[24][64];
+};
+
+__global__ void __launch_bounds__(672, 3) k_sol_half(uint32_t *out, const int32_t *table, int nblk) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    SmemHalf &sm = *reinterpret_cast<SmemHalf *>(raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256 * 32; i += blockDim.x) (&sm.atab[0][0])[i] = table[i];
+    __syncthreads();
+    const int b = blockIdx.x / kCtasPerBlock, g = blockIdx.x - b * kCtasPerBlock;
+    const int r = g * kWarps + warp;
+    if (r >= kRuns) return;
+    double x = 0.001 * lane + 1e-4 * (r & 7), cc = 1.0e-6 * (lane + 1);
+    double y = 3.0 + lane, dd = 0.341 + 1e-6 * lane;
+    const double K43 = 8796093022208.0, K52 = 4503599627370496.0;
+    const double KY = K52 - 3.0;
+    const uint32_t w8 = 0xA5C3F096u ^ (lane * 0x9E3779B9u);
+    const uint32_t abase = (uint32_t) __cvta_generic_to_shared(&sm.atab[0][lane]);
+    int32_t *stage = &sm.stage[warp][0];
+    const size_t samp0 = (size_t) b * kBlockSamples + (size_t) r * kRunSamples;
+    for (int s0 = 0; s0 < kRunSamples; s0 += 64) {
+        const int len = kRunSamples - s0 >= 64 ? 64 : 32;
+#pragma unroll 1
+        for (int g8 = 0; g8 < len; g8 += 8) {
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+                int sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = __double2loint(__dadd_rz(x, K43));
+                    const int rel = __double2loint(__dadd_rz(y, KY));
+                    const int kk = k ^ ((w8 >> (rel & 31)) & 0x100);
+                    int e;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(abase + (uint32_t) (kk & 255) * 128u));
+                    const int m = -((kk >> 8) & 1);                // 0 or -1: negate the packed I + (Q << 16)
+                    e = (e ^ m) - m;
+                    sv[i] = __reduce_add_sync(0xFFFFFFFFu, e);
+                    x = __dadd_rn(x, cc);
+                    y = __dadd_rn(y, dd);
+                }
+                *reinterpret_cast<int4 *>(&stage[g8 + h]) = make_int4(sv[0], sv[1], sv[2], sv[3]);
+            }
+        }
+        __syncwarp();
+        if (len == 64) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int p = stage[lane * 2 + t];
+                const int iv = (int) (short) (p & 0xFFFF), qv = (p - iv) >> 16;
+                const uint32_t two = (((uint32_t) (iv >> 4)) & 0xFFu) | ((((uint32_t) (qv >> 4)) & 0xFFu) << 8);
+                w |= two << (16 * t);
+            }
+            out[(samp0 + s0) / 2 + lane] = w;
+        } else {
+            const int p = stage[lane];
+            const int iv = (int) (short) (p & 0xFFFF), qv = (p - iv) >> 16;
+            reinterpret_cast<uint16_t *>(out)[samp0 + s0 + lane] =
+                (uint16_t) ((((uint32_t) (iv >> 4)) & 0xFFu) | ((((uint32_t) (qv >> 4)) & 0xFFu) << 8));
+        }
+        __syncwarp();
+    }
+}
+
+float run_half(uint32_t *out, const int32_t *tab, int nblk, int reps) {
+    CK(cudaFuncSetAttribute(k_sol_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SmemHalf)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++) k_sol_half<<<nblk * kCtasPerBlock, kWarps * 32, sizeof(SmemHalf)>>>(out, tab, nblk);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++) k_sol_half<<<nblk * kCtasPerBlock, kWarps * 32, sizeof(SmemHalf)>>>(out, tab, nblk);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sol_half, kWarps * 32, sizeof(SmemHalf));
+    printf("{\"formulation\": \"k_synth quiet path, 256-row table, sign applied to the value\", \"blocks\": %d, \"half_table_ms\": %.3f, "
+           "\"ctas_per_sm\": %d}\n", nblk, ms / reps, occ);
+    return ms / reps;
+}
+
 template <bool F>
 float run(uint32_t *out, const int32_t *tab, int nblk, int reps) {
     CK(cudaFuncSetAttribute(k_sol<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -312,6 +404,7 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_out, (size_t) nblk * kBlockSamples * 2));
     const double samples = (double) nblk * kBlockSamples;
+    run_half(d_out, d_tab, nblk, reps);
     const float q = run<false>(d_out, d_tab, nblk, reps), f = run<true>(d_out, d_tab, nblk, reps);
     {
         std::vector<int32_t> t2((size_t) 32 * 512);
