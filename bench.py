@@ -394,7 +394,7 @@ def main():
         probes, span chaining, hand-over, host scan, run checkpoints (+ self-check), synthesis. -> Stats"""
         link = ctx.slice_prepare(chans, ss, dst_ptr, stream=sh, dst_host=dst_host)
         gprn, gph = ho.guessed_incoming(link) if world > 1 else (None, None)
-        ctx.slice_probe(gprn, gph)
+        ctx.slice_probe(gprn, gph, eager=rank + 1 < world)      # a successor waits for this slice's outgoing state
         prn_in, ph_in = ho.recv_exact() if world > 1 else (None, None)
         prn_out, ph_out, st = ctx.slice_finish(prn_in, ph_in, want_stats=True)
         if world > 1:

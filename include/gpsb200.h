@@ -118,6 +118,13 @@ int gpsb200_set_nav(gpsb200_ctx_t *ctx, int frame, int chan, const uint32_t dwrd
 int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                          int sample_size, void *dst, double *carr_phase_out, gpsb200_stats_t *stats);
 
+/* Same, but block b goes to its own host buffer dst_blocks[b] (600000 elements each) -- e.g. buffers handed out by
+ * fifo_acquire(): the device->host copies land straight in iq->data8 / iq->data16 (SURVEY 8b ownership: the producer
+ * owns a buffer between acquire and enqueue), no staging copy on the host. */
+int gpsb200_synth_blocks_scatter(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
+                                 int sample_size, void *const *dst_blocks, double *carr_phase_out,
+                                 gpsb200_stats_t *stats);
+
 /* Same, but the output stays in device memory (dst_device: device pointer with room for
  * nblk * 600000 elements) and the synthesis is only ENQUEUED on `stream` (a cudaStream_t,
  * 0 = the context's own stream) -- the caller synchronizes before reading dst_device. (The
@@ -138,7 +145,7 @@ int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans,
  *                             their links and compose them with gpsb200_link_apply() to obtain good guesses of
  *                             their incoming state without any GPU work.
  *   2. gpsb200_slice_probe    incoming state as GUESSED (NULL: the slice starts the stream): speculative block
- *                             probes + span chaining are enqueued.
+ *                             probes + span chaining are enqueued (all of them at once if `eager`).
  *   3. gpsb200_slice_finish   incoming state EXACT (prn_in/phase_in, from the previous rank's *_out; NULL: the
  *                             stream starts here): segment by segment, as soon as a segment's probes are done, the
  *                             host scan over its span summaries, its run checkpoints (with the device self-check) and
@@ -164,7 +171,12 @@ typedef struct gpsb200_slice_link {
 int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
                           void *dst_device, void *dst_host, void *stream, gpsb200_slice_link_t *link);
 int gpsb200_slice_wait(gpsb200_ctx_t *ctx);
-int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in);
+/* eager != 0: the speculative work of the WHOLE slice is submitted at once, ahead of everything else -- for a rank
+ * whose successor waits for the outgoing state. eager == 0: only the first pipeline segment's; the others follow
+ * segment by segment inside gpsb200_slice_finish, each behind the previous segment's synthesis (in whose shadow the
+ * latency-bound walk kernels then run) and from guesses re-anchored on the exact state just resolved -- for the last
+ * rank and for single-GPU use. */
+int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in, int eager);
 int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
                          double *phase_out, gpsb200_stats_t *stats);
 /* Host only: the link of a slice from its parameters alone (identical to what gpsb200_slice_prepare fills). */
@@ -219,7 +231,8 @@ int gpsb200_span_chain_host(const double *f_carr, int nblk, double start_true, d
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
 
 /* ---- scenario engine: the reference's host path outside the sample loop -------------
- * RINEX-2 navigation file + location/motion -> the gpsb200_chan_t records and NAV frames the
+ * RINEX-2/3 navigation file (plain or gzip-compressed, read through zlib like the reference, gps.c:1147) +
+ * location/motion -> the gpsb200_chan_t records and NAV frames the
  * synthesis consumes; bit-identical to what the reference's producer computes (RINEX reader
  * gps.c:1131-1505, satpos/computeRange/ionosphericDelay gps.c:508-611,1893-2026,
  * computeCodePhase gps.c:2033-2064, eph2sbf/generateNavMsg/computeChecksum gps.c:617-884,
@@ -236,6 +249,10 @@ typedef struct gpsb200_scenario_config {
     int32_t start_year, start_month, start_day, start_hour, start_min;   /* -s; year 0: first ephemeris epoch */
     int32_t rinex3;                /* -3: nav_file is RINEX v3 (gps.c:1512-1891) instead of v2 */
     double start_sec;
+    /* -t distance,bearing,height (gps-sim.c:145-148, gps.c:2348-2357): static runs start at a point given by distance
+     * [m] and bearing [deg] from the location, height offset [m]; ignored with a motion file, as in the reference */
+    int32_t target_valid, reserved;
+    double target_distance_m, target_bearing_deg, target_height_m;
 } gpsb200_scenario_config_t;
 typedef struct gpsb200_scenario gpsb200_scenario_t;
 

@@ -49,7 +49,8 @@ class ScenarioConfig(C.Structure):
                 ("pluto_gain", C.c_int32),
                 ("start_year", C.c_int32), ("start_month", C.c_int32), ("start_day", C.c_int32),
                 ("start_hour", C.c_int32), ("start_min", C.c_int32), ("rinex3", C.c_int32),
-                ("start_sec", C.c_double)]
+                ("start_sec", C.c_double), ("target_valid", C.c_int32), ("reserved", C.c_int32),
+                ("target_distance_m", C.c_double), ("target_bearing_deg", C.c_double), ("target_height_m", C.c_double)]
 
 
 class SliceLink(C.Structure):
@@ -69,7 +70,7 @@ class Stats(C.Structure):
 _lib = None
 
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
-           "gpsb200_synth_blocks", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
+           "gpsb200_synth_blocks", "gpsb200_synth_blocks_scatter", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
            "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_slice_prepare", "gpsb200_slice_probe",
            "gpsb200_slice_finish", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
@@ -119,7 +120,7 @@ def lib():
                                             C.c_void_p, C.POINTER(SliceLink)]
         L.gpsb200_slice_wait.argtypes = [C.c_void_p]
         L.gpsb200_slice_link_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceLink)]
-        L.gpsb200_slice_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gpsb200_slice_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gpsb200_slice_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         L.gpsb200_link_apply.argtypes = [C.POINTER(SliceLink), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gpsb200_debug_corrupt_chain.argtypes = [C.c_void_p, C.c_int]
@@ -194,7 +195,7 @@ def link_apply(link, nchan, prn_in=None, phase_in=None):
 
 
 def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None, start=None,
-             ionosphere=True, pluto_gain=False, rinex3=False):
+             ionosphere=True, pluto_gain=False, rinex3=False, target=None):
     """Run the host scenario engine. -> (chans[nblk, max_chan] CHAN_DTYPE, nav[nframes, max_chan, 60] uint32).
     start: (y, m, d, hh, mm, sec) or None for the first ephemeris epoch."""
     cfg = ScenarioConfig()
@@ -206,6 +207,9 @@ def scenario(nav_file, lat, lon, height, seconds, max_chan=12, motion_file=None,
     cfg.ionosphere_enable = 1 if ionosphere else 0
     cfg.pluto_gain = 1 if pluto_gain else 0
     cfg.rinex3 = 1 if rinex3 else 0
+    if target is not None:          # -t distance,bearing,height
+        cfg.target_valid = 1
+        cfg.target_distance_m, cfg.target_bearing_deg, cfg.target_height_m = [float(v) for v in target]
     if start:
         (cfg.start_year, cfg.start_month, cfg.start_day, cfg.start_hour, cfg.start_min) = [int(v) for v in start[:5]]
         cfg.start_sec = float(start[5])
@@ -308,11 +312,12 @@ class Context:
         self._slice_nchan = nchan
         return link
 
-    def slice_probe(self, prn_in=None, phase_guess_in=None):
+    def slice_probe(self, prn_in=None, phase_guess_in=None, eager=False):
+        """Step 2. eager: all speculative work up front (a successor is waiting for this slice's outgoing state)."""
         pi = None if prn_in is None else np.ascontiguousarray(prn_in, dtype=np.int32)
         xi = None if phase_guess_in is None else np.ascontiguousarray(phase_guess_in, dtype=np.float64)
         self._check(lib().gpsb200_slice_probe(self._h, None if pi is None else pi.ctypes.data,
-                                              None if xi is None else xi.ctypes.data))
+                                              None if xi is None else xi.ctypes.data, 1 if eager else 0))
 
     def slice_finish(self, prn_in=None, phase_in=None, want_stats=False):
         """Step 3. -> (prn_out, phase_out[, Stats]): the exact chain state after the slice."""

@@ -140,6 +140,7 @@ struct gpsb200_ctx {
     double *h_seg_end = nullptr;           // pinned: device-walked end phases of every pipeline segment's last block
     std::vector<double> seg_expect;        // what the chain says they must be
     std::vector<cudaEvent_t> ev_seg;       // slice path: probes of segment i complete
+    void *const *scatter = nullptr;        // gpsb200_synth_blocks_scatter: one host destination per block
     bool fault_inject_chain = false;       // gpsb200_debug_corrupt_chain(): test hook of the device self-check
     // state of a begun, not yet finished call (gpsb200_synth_begin / _finish)
     struct Pending {
@@ -147,7 +148,7 @@ struct gpsb200_ctx {
         int nblk = 0, nchan = 0, sample_size = 0;
         void *dst = nullptr, *dst_host = nullptr;
         cudaStream_t stream = nullptr;
-        bool probed = false, finished = false;
+        bool probed = false, finished = false, eager = false;
         int nseg = 0;
         gpsb200_stats_t st{};
     } pending;
@@ -290,6 +291,29 @@ void finalize_guesses(gpsb200_ctx *ctx, int b0, int b1, int nchan, const int32_t
                 if (ctx->h_guess_abs[i] || ctx->h_bc[i].prn <= 0) continue;
                 double g = ctx->h_guess[i] + off;
                 if (g >= 1.0) g -= 1.0;
+                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                ctx->h_guess[i] = g;
+            }
+        }
+    });
+}
+
+// The exact chain state after block b0-1 is known: move the guesses of blocks [b0, b1) by the error the guess of
+// block b0 turned out to have (a slot's guesses are corrected up to its next (re)allocation, whose phase is exact).
+void reanchor_guesses(gpsb200_ctx *ctx, int b0, int b1, int nchan, const std::vector<ChainState> &chain) {
+    ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
+        for (int c = c_lo; c < c_hi; c++) {
+            const BlockChanDev &first = ctx->h_bc[(size_t) b0 * nchan + c];
+            if (first.prn <= 0 || chain[c].prn != first.prn) continue;     // starts from an allocation phase: exact already
+            double delta = chain[c].phase - ctx->h_guess[(size_t) b0 * nchan + c];
+            if (delta > 0.5) delta -= 1.0;
+            if (delta < -0.5) delta += 1.0;
+            for (int b = b0; b < b1; b++) {
+                const size_t i = (size_t) b * nchan + c;
+                if (ctx->h_bc[i].prn != first.prn) break;
+                double g = ctx->h_guess[i] + delta;
+                if (g >= 1.0) g -= 1.0;
+                if (g < 0.0) g += 1.0;
                 if (!(g >= 0.0 && g < 1.0)) g = 0.0;
                 ctx->h_guess[i] = g;
             }
@@ -522,6 +546,7 @@ int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp
 }
 
 // Synthesis of blocks [b0, b1) in chunks, each chunk's download to dst_host enqueued on s_copy behind it.
+// dst_host is either one contiguous buffer or, when ctx->scatter is set, ignored in favour of one host address per block.
 int synth_chunks(gpsb200_ctx *ctx, int b0, int b1, int nchan, int sample_size, void *dst_dev, void *dst_host,
                  cudaStream_t s, gpsb200_stats_t &st, int &ichunk) {
     const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
@@ -537,8 +562,14 @@ int synth_chunks(gpsb200_ctx *ctx, int b0, int b1, int nchan, int sample_size, v
         st.launches += 1;
         CU(cudaEventRecord(ctx->ev_done[ichunk], s));
         CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[ichunk], 0));
-        CU(cudaMemcpyAsync((char *) dst_host + (size_t) c0 * blk_bytes, dout, (size_t) nc * blk_bytes,
-                           cudaMemcpyDeviceToHost, ctx->s_copy));
+        if (ctx->scatter) {          // every block straight into its own (FIFO) buffer
+            for (int b = c0; b < c0 + nc; b++)
+                CU(cudaMemcpyAsync(ctx->scatter[b], dout + (size_t) (b - c0) * blk_bytes, blk_bytes, cudaMemcpyDeviceToHost,
+                                   ctx->s_copy));
+        } else {
+            CU(cudaMemcpyAsync((char *) dst_host + (size_t) c0 * blk_bytes, dout, (size_t) nc * blk_bytes,
+                               cudaMemcpyDeviceToHost, ctx->s_copy));
+        }
         st.d2h_bytes += (int64_t) nc * (int64_t) blk_bytes;
     }
     return GPSB200_OK;
@@ -1018,7 +1049,7 @@ int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int n
     return GPSB200_OK;
 }
 
-int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in) {
+int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in, int eager) {
     if (!ctx) return GPSB200_ERR_ARG;
     if (!ctx->pending.active || ctx->pending.probed)
         return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_probe: call gpsb200_slice_prepare first");
@@ -1028,7 +1059,9 @@ int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double 
     finalize_guesses(ctx, 0, nblk, nchan, prn_in, phase_guess_in);
     ctx->pending.st.host_chain_ms += now_ms() - t0;
     int rc = GPSB200_OK, iseg = 0;
-    for (const auto &sg : segments_of(nblk)) {          // speculative work of every segment, in stream order
+    ctx->pending.eager = eager != 0;
+    for (const auto &sg : segments_of(nblk)) {          // speculative work: every segment now (eager), or the first
+        if (!ctx->pending.eager && iseg > 0) break;     // one only -- the others follow one by one in _finish
         SynthArgs a{};
         fill_args(ctx, a, sg.first, sg.second - sg.first, nchan, ctx->pending.sample_size, nullptr);
         rc = segment_probe(ctx, sg.first, sg.second, nchan, ctx->s_pre, ctx->pending.st, sg.first == 0, a);
@@ -1074,6 +1107,17 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
         } else {
             CU(launch_synth(a, s));
             st.launches += 1;
+        }
+        if (!ctx->pending.eager && b1 < nblk) {
+            // lazy: the next segment's speculative work is submitted only now, BEHIND this segment's synthesis (it
+            // runs in its shadow), from guesses re-anchored on the exact state just resolved
+            const int n1 = std::min(nblk, b1 + kSegBlocks);
+            reanchor_guesses(ctx, b1, n1, nchan, chain);
+            SynthArgs an{};
+            fill_args(ctx, an, b1, n1 - b1, nchan, sample_size, nullptr);
+            rc = segment_probe(ctx, b1, n1, nchan, ctx->s_pre, st, false, an);
+            if (rc) return rc;
+            CU(cudaEventRecord(ctx->ev_seg[iseg], ctx->s_pre));
         }
     }
     ctx->pending.nseg = iseg;
@@ -1235,6 +1279,17 @@ int gpsb200_replay_device(gpsb200_ctx_t *ctx, void *dst_device, void *stream_, i
     if (kernel_mask & 1) CU(launch_checkpoints(a, s));
     if (kernel_mask & 2) CU(launch_synth(a, s));
     return GPSB200_OK;
+}
+
+int gpsb200_synth_blocks_scatter(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,
+                                 void *const *dst_blocks, double *carr_phase_out, gpsb200_stats_t *stats) {
+    if (!ctx || !dst_blocks) return GPSB200_ERR_ARG;
+    for (int b = 0; b < nblk; b++)
+        if (!dst_blocks[b]) return fail(ctx, GPSB200_ERR_ARG, "gpsb200_synth_blocks_scatter: NULL block destination");
+    ctx->scatter = dst_blocks;
+    const int rc = gpsb200_synth_blocks(ctx, chans, nblk, nchan, sample_size, dst_blocks[0], carr_phase_out, stats);
+    ctx->scatter = nullptr;
+    return rc;
 }
 
 int gpsb200_synth_blocks(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size,

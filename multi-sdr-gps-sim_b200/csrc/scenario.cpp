@@ -25,6 +25,8 @@
 #include <thread>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/gpsb200.h"
 #include "synth_tables.h"
 
@@ -499,11 +501,11 @@ void fill_orbit(Eph &e, const std::string l[7], int c0) {
 }
 
 int read_rinex2(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
-    FILE *fp = fopen(path, "rt");
+    gzFile fp = gzopen(path, "rt");                   // plain text or .gz, like the reference (gps.c:1147)
     if (!fp) return -1;
     char buf[256];
     auto next = [&](std::string &out) -> bool {
-        if (!fgets(buf, 100, fp)) return false;       // MAX_CHAR = 100 (gps.h:30)
+        if (!gzgets(fp, buf, 100)) return false;      // MAX_CHAR = 100 (gps.h:30)
         out = buf;
         return true;
     };
@@ -514,7 +516,7 @@ int read_rinex2(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
         if (label_is(ln, "END OF HEADER")) break;
         if (label_is(ln, "RINEX VERSION / TYPE")) {
             if (field(ln, 0, 9) > 3.0 || ln.size() <= 20 || ln[20] != 'N') {
-                fclose(fp);
+                gzclose(fp);
                 return -2;
             }
         } else if (label_is(ln, "ION ALPHA")) {
@@ -566,18 +568,18 @@ int read_rinex2(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
         if (!ok) break;
         fill_orbit(e, l, 3);
     }
-    fclose(fp);
+    gzclose(fp);
     if (g0.week >= 0) ieph += 1;
-    return ieph;
-}
+    return ieph > kEphSets ? kEphSets : ieph;      // a file with more than 13 hourly sets: the table is full (the
+}                                                   // reference returns 14 there and reads past its array)
 
 // ---- RINEX v3 navigation reader (gps.c:1512-1891): GPS records only ------------------------------------------
 int read_rinex3(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
-    FILE *fp = fopen(path, "rt");
+    gzFile fp = gzopen(path, "rt");                   // gps.c:1528
     if (!fp) return -1;
     char buf[256];
     auto next = [&](std::string &out) -> bool {
-        if (!fgets(buf, 100, fp)) return false;
+        if (!gzgets(fp, buf, 100)) return false;
         out = buf;
         return true;
     };
@@ -588,7 +590,7 @@ int read_rinex3(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
         if (label_is(ln, "END OF HEADER")) break;
         if (label_is(ln, "RINEX VERSION / TYPE")) {
             if (field(ln, 0, 9) < 3.0 || ln.size() <= 40 || (ln[20] != 'N' && ln[40] != 'G')) {
-                fclose(fp);
+                gzclose(fp);
                 return -2;
             }
         } else if (label_is(ln, "IONOSPHERIC CORR")) {
@@ -643,7 +645,7 @@ int read_rinex3(const char *path, Eph eph[kEphSets][kMaxSat], IonoUtc &io) {
         if (!ok) break;
         fill_orbit(e, l, 4);
     }
-    fclose(fp);
+    gzclose(fp);
     if (g0.week >= 0) ieph += 1;
     return ieph;
 }
@@ -700,6 +702,19 @@ int build(gpsb200_scenario *S) {
     } else {
         xyz.resize(3);
         llh_to_ecef(llh, xyz.data());
+        if (cfg.target_valid) {
+            // -t distance,bearing,height: start at a point given relative to the location (gps.c:2348-2357). The CLI
+            // stores the bearing in millidegrees (gps-sim.c:148) and the producer divides it back: same round trip here.
+            double t[3][3], neu[3];
+            local_frame(llh, t);
+            const double bearing_milli = cfg.target_bearing_deg * 1000;
+            neu[0] = cfg.target_distance_m * cos((bearing_milli / 1000) / kR2D);
+            neu[1] = cfg.target_distance_m * sin((bearing_milli / 1000) / kR2D);
+            neu[2] = cfg.target_height_m;
+            xyz[0] += t[0][0] * neu[0] + t[1][0] * neu[1] + t[2][0] * neu[2];
+            xyz[1] += t[0][1] * neu[0] + t[1][1] * neu[1] + t[2][1] * neu[2];
+            xyz[2] += t[0][2] * neu[0] + t[1][2] * neu[1] + t[2][2] * neu[2];
+        }
     }
     auto pos_at = [&](int i) -> const double * { return xyz.size() > 3 ? &xyz[3 * (size_t) i] : xyz.data(); };
     if (numd < 2) return fail(S, "duration too short");

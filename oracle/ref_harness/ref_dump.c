@@ -168,6 +168,11 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "-s") && i + 1 < argc)
             sscanf(argv[++i], "%d/%d/%d,%d:%d:%lf", &sim.start.y, &sim.start.m, &sim.start.d,
                    &sim.start.hh, &sim.start.mm, &sim.start.sec);
+        else if (!strcmp(argv[i], "-t") && i + 1 < argc) {                 /* as gps-sim.c:145-148 */
+            sim.target.valid = true;
+            sscanf(argv[++i], "%lf,%lf,%lf", &sim.target.distance, &sim.target.bearing, &sim.target.height);
+            sim.target.bearing *= 1000;
+        }
         else if (!strcmp(argv[i], "--iq16")) sim.sample_size = SC16;
         else if (!strcmp(argv[i], "-3")) sim.use_rinex3 = true;
         else if (!strcmp(argv[i], "--pluto-gain")) sim.sdr_type = SDR_PLUTOSDR;

@@ -54,6 +54,8 @@ SCENARIOS["sky12_ephroll_400s_i8"] = (12, "ref_dump12", 400, [], [])
 SCENARIOS["sky12_circle_60s_i16"] = (12, "ref_dump12", 60, ["--iq16", "-m", "/root/reference/circle.csv"], [])
 # ADALM-Pluto flavour of the sample loop: gain x 2 (gps.c:2759-2763), int16 (sdr_pluto.c:107-110)
 SCENARIOS["sky12_pluto_3s_i16"] = (12, "ref_dump12", 3, ["--iq16", "--pluto-gain"], [0])
+# -t distance,bearing,height: static start point relative to the location (gps.c:2348-2357)
+SCENARIOS["sky12_target_3s_i8"] = (12, "ref_dump12", 3, ["-t", "1500.5,33.3,120.25"], [])
 LOCS = {"sky32_lat60_310s_i8": "60.0,140.0,0.0"}
 STARTS = {"sky12_ephroll_400s_i8": "2024/01/07,02:55:00"}
 RINEX_ARGS = {"sky12_ephroll_400s_i8": ["--sets", "2"]}

@@ -553,8 +553,8 @@ def _three_step_slices(ch, nav, edges, sample_size=1):
             outs.append(dev)
             links.append(ctx.slice_prepare(ch[lo:hi], sample_size, dev.data_ptr()))
         prn, ph = None, None
-        for ctx, link in zip(ctxs, links):                    # guesses: closed form only, no GPU result involved
-            ctx.slice_probe(prn, ph)
+        for k, (ctx, link) in enumerate(zip(ctxs, links)):    # guesses: closed form only, no GPU result involved
+            ctx.slice_probe(prn, ph, eager=k + 1 < len(ctxs))
             prn, ph = gps.link_apply(link, nchan, prn, ph)
         prn, ph, fallbacks = None, None, 0
         for ctx in ctxs:                                      # exact states, rank to rank
@@ -641,7 +641,7 @@ def test_config4_3600s_32ch_sliced_8_ways_equals_reference_stream(tmp_path):
             with gps.Context(nchan, hi - lo, max_nav_frames=len(nav)) as ctx:      # one "rank" at a time: 2.7 GB each
                 ctx.set_nav_frames(nav)
                 ctx.slice_prepare(ch[lo:hi], 1, dev.data_ptr())
-                ctx.slice_probe(gprn, gph)
+                ctx.slice_probe(gprn, gph, eager=hi < ch.shape[0])
                 eprn, eph, st = ctx.slice_finish(eprn, eph, want_stats=True)
                 ctx.slice_wait()
                 assert st.chain_fallbacks < 0.01 * (hi - lo) * nchan
@@ -654,3 +654,44 @@ def test_config4_3600s_32ch_sliced_8_ways_equals_reference_stream(tmp_path):
             c.close()
     assert bad_total == 0
     assert np.array_equal(eph, gps.carrier_chain(ch, threads=16))
+
+
+def test_target_option_static_start_point_matches_reference_stream(tmp_path):
+    """-t distance,bearing,height (gps-sim.c:145-148, gps.c:2348-2357): scenario engine + synthesis against the
+    reference run with the same option."""
+    g = scenario.load_golden("sky12_target_3s_i8")
+    ch, nav = gps.scenario(_nav_file(tmp_path, 12), 35.681298, 139.766247, 10.0, seconds=3, max_chan=12,
+                           start=(2024, 1, 7, 2, 0, 0.0), target=(1500.5, 33.3, 120.25))
+    with gps.Context(12, ch.shape[0], max_nav_frames=len(nav)) as ctx:
+        ctx.set_nav_frames(nav)
+        out, _ = ctx.synth_blocks(ch, 1)
+    assert np.array_equal(scenario.crc_blocks(out), g["crcs"][:, 0])
+
+
+def test_cli_multi_gpu_slices_write_the_reference_stream(tmp_path):
+    """gpsb200-sim --gpus N (one worker thread + context per device, slices handed over with the three-step API, one
+    FIFO sink in stream order) and the zero-copy single-GPU path with -t: CRC-equal to the reference goldens.
+    N = 2 when two devices are visible, else the N = 1 paths only."""
+    import os
+    import subprocess
+    import zlib
+    import torch
+    exe = os.path.join(scenario.ROOT, "multi-sdr-gps-sim_b200", "gpsb200-sim")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(scenario.ROOT, "multi-sdr-gps-sim_b200", "csrc")])
+    nav = _nav_file(tmp_path, 12)
+    base = [exe, "-e", nav, "-l", "35.681298,139.766247,10.0", "-s", "2024/01/07,02:00:00"]
+    g = scenario.load_golden("sky12_static_35s_i8")
+    counts = [1] + ([2] if torch.cuda.device_count() >= 2 else [])
+    for n in counts:
+        out = tmp_path / ("iq_%d.bin" % n)
+        subprocess.check_call(base + ["-d", "35", "--gpus", str(n), "-o", str(out)])
+        s = np.fromfile(out, dtype=np.int8).reshape(-1, gps.BLOCK_ELEMS)
+        assert s.shape[0] == 349
+        bad = [b for b, row in enumerate(s) if zlib.crc32(row.tobytes()) != g["crcs"][b, 0]]
+        assert not bad, (n, bad[:5])
+    gt = scenario.load_golden("sky12_target_3s_i8")
+    out = tmp_path / "iq_t.bin"
+    subprocess.check_call(base + ["-d", "3", "-t", "1500.5,33.3,120.25", "-o", str(out)])
+    s = np.fromfile(out, dtype=np.int8).reshape(-1, gps.BLOCK_ELEMS)
+    assert [zlib.crc32(r.tobytes()) for r in s] == list(gt["crcs"][:, 0])

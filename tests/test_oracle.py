@@ -135,3 +135,7 @@ def test_oracle_pluto_gain_int16_bit_exact():
 def test_oracle_config3_circle_60s_first_blocks():
     """configs[3] literally (circle.csv, --iq16, 60 s): the fixture keeps the first two blocks' parameters."""
     run_scenario("sky12_circle_60s_i16", nblocks=2)
+
+
+def test_oracle_target_option_bit_exact():
+    run_scenario("sky12_target_3s_i8")

@@ -19,6 +19,7 @@ CASES = {
     "sky12_circle_10s_i16": dict(nsat=12, chan=12, secs=10, motion=True),
     "sky12_rinex3_3s_i8": dict(nsat=12, chan=12, secs=3, v3=True),
     "sky12_pluto_3s_i16": dict(nsat=12, chan=12, secs=3, pluto=True),
+    "sky12_target_3s_i8": dict(nsat=12, chan=12, secs=3, target=(1500.5, 33.3, 120.25)),     # -t (gps.c:2348-2357)
 }
 
 
@@ -47,7 +48,7 @@ def test_scenario_engine_matches_reference_dump_bit_for_bit(name, tmp_path):
     mot = motion_file(tmp_path) if c.get("motion") else None
     got, nav = gps.scenario(make_nav(tmp_path, c["nsat"], c.get("v3", False)), *LOC, seconds=c["secs"],
                             max_chan=c["chan"], motion_file=mot, start=START, rinex3=c.get("v3", False),
-                            pluto_gain=c.get("pluto", False))
+                            pluto_gain=c.get("pluto", False), target=c.get("target"))
     assert got.shape == want.shape
     assert np.array_equal(got["prn"], want["prn"])
     act = want["prn"] > 0
@@ -158,3 +159,16 @@ def test_config3_circle_csv_60s_engine_matches_dump(tmp_path):
     if os.path.exists(src):            # the re-written rows parse to the same doubles as the original file
         ref, _ = gps.scenario(make_nav(tmp_path, 12), *LOC, seconds=60, max_chan=12, motion_file=src, start=START)
         assert got.tobytes() == ref.tobytes()
+
+
+def test_gzip_compressed_rinex_reads_like_the_plain_file(tmp_path):
+    """The reference reads its navigation files through zlib (gzopen/gzgets, gps.c:1147-1157): .gz or plain."""
+    import gzip
+    import shutil
+    for v3 in (False, True):
+        nav = make_nav(tmp_path, 12, v3=v3)
+        with open(nav, "rb") as fi, gzip.open(nav + ".gz", "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        a, na = gps.scenario(nav, *LOC, seconds=2, max_chan=12, start=START, rinex3=v3)
+        b, nb = gps.scenario(nav + ".gz", *LOC, seconds=2, max_chan=12, start=START, rinex3=v3)
+        assert a.tobytes() == b.tobytes() and na.tobytes() == nb.tobytes()
