@@ -392,6 +392,11 @@ def main():
     def one_step(dst_ptr=0, dst_host=None):
         """One pass of the whole hot path over this rank's slice: host records, parameters up, carrier tables, block
         probes, span chaining, hand-over, host scan, run checkpoints (+ self-check), synthesis. -> Stats"""
+        if world == 1 and dst_host is None:
+            # one GPU: the public device-destination call (the same steps, pipelined segment by segment; it returns
+            # once everything is enqueued and the chain self-check of the whole call has been read)
+            ph, st1 = ctx.synth_blocks_device(chans, ss, dst_ptr, stream=sh, want_stats=True)
+            return st1, ph
         link = ctx.slice_prepare(chans, ss, dst_ptr, stream=sh, dst_host=dst_host)
         gprn, gph = ho.guessed_incoming(link) if world > 1 else (None, None)
         ctx.slice_probe(gprn, gph, eager=rank + 1 < world)      # a successor waits for this slice's outgoing state
@@ -403,8 +408,14 @@ def main():
 
     # ---- value: the whole path, parameters in host memory (6 MB), result left in HBM ---------------------
     note("value leg: first full pass")
+    def step_wait():
+        if world == 1:
+            stream.synchronize()
+        else:
+            ctx.slice_wait()          # completion + verdict of the device self-check
+
     st, _ = one_step(out_dev.data_ptr())
-    ctx.slice_wait()
+    step_wait()
     sampler = None
     if rank == 0:
         uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
@@ -412,7 +423,7 @@ def main():
     note("value leg: %d warm-up + %d timed steps" % (args.warmup, args.steps))
     for _ in range(args.warmup):
         one_step(out_dev.data_ptr())
-        ctx.slice_wait()
+        step_wait()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"k_probe_chain_ms": 0.0, "k_checkpoints_ms": 0.0, "k_synth_ms": 0.0, "host_chain_ms": 0.0}
@@ -421,7 +432,7 @@ def main():
     ev0.record(stream)
     for i in range(args.steps):
         st, ph_last = one_step(out_dev.data_ptr())
-        ctx.slice_wait()                                      # completion + self-check verdict; the buffers are reused
+        step_wait()                                           # the buffers are reused by the next step
         kern["host_chain_ms"] += st.host_chain_ms
         fallbacks += st.chain_fallbacks
     ev1.record(stream)

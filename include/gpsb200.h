@@ -288,7 +288,9 @@ struct iq_buf *fifo_dequeue(void);
 void fifo_release(struct iq_buf *buf);
 #endif /* FIFO_H */
 /* gpsb200 extension: reproduce the stock reference's loss of buffers 1..6 of a run
- * (tail bug, fifo.c:163-168) so that iqdata.bin is byte-identical to the stock program. */
+ * (tail bug, fifo.c:163-168) so that iqdata.bin is byte-identical to the stock program. The guarantee covers that
+ * start-up loss with the reference's geometry (8 buffers, writer started when the FIFO is primed); as in the stock
+ * program, further losses while the consumer lags depend on producer/consumer timing. */
 void fifo_set_compat_drop(bool on);
 
 /* Feed a contiguous run of I/Q elements into FIFO buffers of whatever size the FIFO was created

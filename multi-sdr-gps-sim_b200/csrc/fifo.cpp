@@ -8,7 +8,9 @@
 //     synthesis result is copied device->host straight into data8/data16;
 //   * fifo_enqueue links at the tail AND advances it (the reference forgets to move
 //     fifo_tail, fifo.c:163-168, which silently drops buffers 1..6 of a run);
-//     fifo_set_compat_drop(true) restores that loss for byte-identical iqdata.bin;
+//     fifo_set_compat_drop(true) restores that loss for byte-identical iqdata.bin (guaranteed for the start-up
+//     loss of buffers 1..6 with the reference's 8-buffer geometry; like the stock program, which later buffers are
+//     lost once the consumer lags depends on timing);
 //   * waits are `while` loops (the reference uses `if`, fifo.c:132-136,178-181).
 #include <cuda_runtime_api.h>
 
@@ -21,6 +23,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../../include/gpsb200.h"
 
@@ -31,26 +34,32 @@ std::condition_variable g_notempty, g_empty, g_free, g_full;
 iq_buf *g_head = nullptr, *g_tail = nullptr, *g_freelist = nullptr;
 bool g_halted = false;
 bool g_compat_drop = false;
-bool g_pinned = false;
 bool g_full_signalled = false;
+std::vector<void *> g_pinned_ptrs;      // which sample buffers are page-locked (the rest came from calloc); under g_mu
 
 void *alloc_bytes(size_t n) {
     void *p = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 &&
         cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess) {
-        g_pinned = true;
+        g_pinned_ptrs.push_back(p);
         memset(p, 0, n);
         return p;
     }
-    cudaGetLastError();
+    cudaGetLastError();                  // no device, or the page-locked pool is exhausted: ordinary memory
     return calloc(1, n);
 }
 
 void free_bytes(void *p) {
     if (!p) return;
-    if (g_pinned) cudaFreeHost(p);
-    else free(p);
+    for (size_t i = 0; i < g_pinned_ptrs.size(); i++)
+        if (g_pinned_ptrs[i] == p) {
+            g_pinned_ptrs[i] = g_pinned_ptrs.back();
+            g_pinned_ptrs.pop_back();
+            cudaFreeHost(p);
+            return;
+        }
+    free(p);
 }
 
 void free_list(iq_buf *h) {
@@ -85,11 +94,14 @@ bool fifo_create(unsigned buffer_count, unsigned buffer_size, unsigned sample_si
     g_full_signalled = false;
     for (unsigned i = 0; i < buffer_count; i++) {
         iq_buf *b = (iq_buf *) calloc(1, sizeof(iq_buf));
-        if (!b) return false;
-        if (sample_size == sizeof(signed short)) b->data16 = (signed short *) alloc_bytes((size_t) buffer_size * 2);
-        else b->data8 = (signed char *) alloc_bytes((size_t) buffer_size);
-        if (!b->data8 && !b->data16) {
+        if (b) {
+            if (sample_size == sizeof(signed short)) b->data16 = (signed short *) alloc_bytes((size_t) buffer_size * 2);
+            else b->data8 = (signed char *) alloc_bytes((size_t) buffer_size);
+        }
+        if (!b || (!b->data8 && !b->data16)) {         // release what was created so far (fifo.c:60 calls fifo_destroy)
             free(b);
+            free_list(g_freelist);
+            g_freelist = nullptr;
             return false;
         }
         b->totalLength = buffer_size;

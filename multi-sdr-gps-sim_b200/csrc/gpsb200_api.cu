@@ -137,7 +137,8 @@ struct gpsb200_ctx {
     SpanBlockState *d_spec = nullptr;                  // speculative block-start phases
     SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
     int max_spans = 0, max_segs = 0;
-    double *h_seg_end = nullptr;           // pinned: device-walked end phases of every pipeline segment's last block
+    double *h_seg_end = nullptr, *d_seg_end = nullptr;   // mapped: device-walked end phases of every pipeline segment's last block
+    int cur_seg = 0;                       // which row of h_seg_end the next checkpoint launch fills
     std::vector<double> seg_expect;        // what the chain says they must be
     std::vector<cudaEvent_t> ev_seg;       // slice path: probes of segment i complete
     void *const *scatter = nullptr;        // gpsb200_synth_blocks_scatter: one host destination per block
@@ -539,7 +540,9 @@ int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp
         CU(cudaMemcpyAsync(ctx->d_carr0 + off, ctx->h_carr0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
         st.h2d_bytes += (int64_t) (cnt * sizeof(double));
     }
-    CU(launch_checkpoints(a, sp));
+    SynthArgs ack = a;
+    ack.last_end_host = ctx->cur_seg < ctx->max_segs ? ctx->d_seg_end + (size_t) ctx->cur_seg * nchan : nullptr;
+    CU(launch_checkpoints(ack, sp));
     if (first) CU(cudaEventRecord(ctx->ev[4], sp));
     st.launches += 1;
     return GPSB200_OK;
@@ -610,9 +613,8 @@ int note_segment_end(gpsb200_ctx *ctx, int iseg, int b1, int nchan, cudaStream_t
         const bool live = chain[c].prn > 0 && ctx->h_bc[(size_t) (b1 - 1) * nchan + c].prn == chain[c].prn;
         ctx->seg_expect[(size_t) iseg * nchan + c] = live ? chain[c].phase : -1.0;       // -1: nothing to compare
     }
-    CU(cudaMemcpyAsync(ctx->h_seg_end + (size_t) iseg * nchan, ctx->d_carr_end + (size_t) (b1 - 1) * nchan,
-                       (size_t) nchan * sizeof(double), cudaMemcpyDeviceToHost, sp));
-    return GPSB200_OK;
+    (void) sp;       // the checkpoint kernel of the segment stores its last block's end phases into h_seg_end itself
+    return GPSB200_OK;   // (mapped memory: a copy-engine transfer would queue behind the large result downloads)
 }
 
 // Verdict of the device self-check (all of sp's work must be complete): the per-block comparisons inside the
@@ -657,6 +659,7 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
         if (rc) return rc;
         rc = segment_probe(ctx, b0, b1, nchan, sp, st, b0 == 0, a);
         if (rc) return rc;
+        ctx->cur_seg = iseg;
         rc = segment_resolve(ctx, b0, b1, nchan, sp, chain, st, b0 == 0, a);
         if (rc) return rc;
         rc = note_segment_end(ctx, iseg++, b1, nchan, sp, chain);
@@ -891,7 +894,8 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     ctx->max_segs = (c.max_blocks + kSegBlocks - 1) / kSegBlocks + 2;
     ctx->ev_seg.resize(ctx->max_segs);
     for (auto &e : ctx->ev_seg) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaHostAlloc(&ctx->h_seg_end, (size_t) ctx->max_segs * c.max_chan * sizeof(double), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&ctx->h_seg_end, (size_t) ctx->max_segs * c.max_chan * sizeof(double), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **) &ctx->d_seg_end, ctx->h_seg_end, 0));
     ctx->seg_expect.assign((size_t) ctx->max_segs * c.max_chan, -1.0);
     const size_t nbc = (size_t) c.max_blocks * c.max_chan;
     CU(cudaMalloc(&ctx->d_bc, nbc * sizeof(BlockChanDev)));
@@ -1094,6 +1098,7 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
         fill_args(ctx, a, b0, b1 - b0, nchan, sample_size, (char *) ctx->pending.dst + (size_t) b0 * blk_bytes);
         // host scan of this segment as soon as ITS probes are done; checkpoints on a stream of their own, so that
         // they do not queue behind the probes of later segments; the synthesis follows on the caller's stream
+        ctx->cur_seg = iseg;
         int rc = segment_resolve(ctx, b0, b1, nchan, sk, chain, st, b0 == 0, a, ctx->ev_seg[iseg]);
         if (rc) return rc;
         rc = note_segment_end(ctx, iseg++, b1, nchan, sk, chain);

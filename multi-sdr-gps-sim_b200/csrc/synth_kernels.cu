@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
         nco_advance<NCO_CARRIER>(x, p.c_carr, a.run_samples, dummy);
     }
     if (a.carr_end) a.carr_end[(size_t) b * a.nchan + c] = x;
+    if (a.last_end_host && b == a.nblk - 1) a.last_end_host[c] = x;
     // Self-check of the parallel-in-time chain: the phase this exact walk ends on must BE the start phase the
     // two-level speculation resolved for the next block of the same satellite in this launch.
     if (a.chain_errors && p.prn > 0 && b + 1 < a.nblk && a.bc[(size_t) (b + 1) * a.nchan + c].prn == p.prn &&

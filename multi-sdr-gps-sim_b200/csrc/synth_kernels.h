@@ -60,6 +60,8 @@ struct SynthArgs {
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
     int32_t *atab;            // [nblk][513][32] gain-scaled carrier table per block: I + (Q << 16), column = lane
     double *carr_end;         // [nblk][nchan] carrier phase after the block
+    double *last_end_host;    // [nchan], mapped host memory: carrier phase after the LAST block of this launch (self-check
+                              // across launches; written by the kernel so that no copy-engine transfer is needed)
     int *chain_errors;        // self-check counter: blocks whose walked end phase != the next block's start phase
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
