@@ -135,6 +135,10 @@ struct gpsb200_ctx {
     CarrierProbe *h_probe = nullptr, *d_probe_host = nullptr;   // ... and in mapped host memory (host fallback)
     CarrierProbe *h_span_sum = nullptr, *d_span_sum = nullptr;  // span summaries, mapped host memory
     SpanBlockState *d_spec = nullptr;                  // speculative block-start phases
+    double *d_run_x = nullptr;                         // run-start states of the block probes' variant trajectories
+    double *d_blk_shift = nullptr, *h_blk_shift = nullptr;     // host-resolved spans: per-block shift / variant pick
+    int32_t *d_blk_pick = nullptr, *h_blk_pick = nullptr;
+    int check_stride = 8, check_phase = 0;             // sampled exact re-walk of the chain (GPSB200_CHECK_STRIDE)
     SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
     int max_spans = 0, max_segs = 0;
     double *h_seg_end = nullptr, *d_seg_end = nullptr;   // mapped: device-walked end phases of every pipeline segment's last block
@@ -196,8 +200,11 @@ double now_ms() {
 // guesses are accumulated RELATIVE to it (h_guess holds the advance since the slice start, h_guess_abs marks
 // blocks after a (re)allocation inside the slice, whose guesses are absolute) and finalize_guesses() adds the
 // offset later; *link describes how the slice maps an incoming state to the guessed outgoing one.
+// end_guess (optional): the GUESSED chain state after block b1-1, to seed the guesses of the next segment when that
+// is prepared before this one has been resolved.
 int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan,
-                   const std::vector<ChainState> &chain, gpsb200_slice_link_t *link = nullptr) {
+                   const std::vector<ChainState> &chain, gpsb200_slice_link_t *link = nullptr,
+                   std::vector<ChainState> *end_guess = nullptr) {
     const double delt = 1.0 / (double) GPSB200_SAMPLERATE;     // gps.c:2298
     std::vector<int> status(nchan, GPSB200_OK);
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
@@ -258,6 +265,12 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 acc += (long double) GPSB200_BLOCK_SAMPLES *
                        ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
                 acc -= floorl(acc);
+            }
+            if (end_guess) {
+                double g = (double) acc;
+                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
+                (*end_guess)[c].prn = prev_prn > 0 ? prev_prn : 0;
+                (*end_guess)[c].phase = prev_prn > 0 ? g : 0.0;
             }
             if (link) {
                 link->prn_last[c] = prev_prn > 0 ? prev_prn : 0;
@@ -324,7 +337,10 @@ void reanchor_guesses(gpsb200_ctx *ctx, int b0, int b1, int nchan, const std::ve
 
 // One block of the chain, resolved on the host from its block probe (the first level of the speculation);
 // the exact sequential walk when the probe cannot be used. Returns 1 when it had to walk.
-inline int resolve_block(ChainState &st, const BlockChanDev &bc, const CarrierProbe &probe, double &start_out) {
+inline int resolve_block(ChainState &st, const BlockChanDev &bc, const CarrierProbe &probe, double &start_out,
+                         int32_t &pick_out, double &shift_out) {
+    pick_out = -1;                       // -1: k_checkpoints walks the block exactly
+    shift_out = 0.0;
     if (bc.prn <= 0) {
         st.prn = 0;
         start_out = 0.0;
@@ -333,9 +349,12 @@ inline int resolve_block(ChainState &st, const BlockChanDev &bc, const CarrierPr
     if (st.prn != bc.prn) st.phase = bc.carr_in;
     st.prn = bc.prn;
     start_out = st.phase;
-    double xe;
-    if (carrier_fixup(st.phase, bc.c_carr, probe, xe)) {
+    double xe, d;
+    int v;
+    if (carrier_fixup(st.phase, bc.c_carr, probe, xe, &v, &d)) {
         st.phase = xe;
+        pick_out = v;
+        shift_out = d;
         return 0;
     }
     int64_t dummy = 0;
@@ -394,7 +413,8 @@ int64_t resolve_chain(gpsb200_ctx *ctx, int b0, int b1, int nchan, std::vector<C
                 ++slow[c];
                 for (int b = s0; b < s1; b++) {
                     const size_t i = (size_t) b * nchan + c;
-                    fallbacks[c] += resolve_block(st, ctx->h_bc[i], ctx->h_probe[i], ctx->h_carr0[i]);
+                    fallbacks[c] += resolve_block(st, ctx->h_bc[i], ctx->h_probe[i], ctx->h_carr0[i], ctx->h_blk_pick[i],
+                                                  ctx->h_blk_shift[i]);
                 }
             }
             chain[c] = st;
@@ -405,10 +425,7 @@ int64_t resolve_chain(gpsb200_ctx *ctx, int b0, int b1, int nchan, std::vector<C
     if (ctx->fault_inject_chain && b1 - b0 > 6) {
         SpanRes &r = ctx->h_span_res[(size_t) (b0 / K) * nchan];
         if (r.mode == 0) r.shift += 0x1p-51;
-        else if (r.mode == 1) {
-            double &v = ctx->h_carr0[(size_t) (b0 + 5) * nchan];
-            v = bits_f64(f64_bits(v) ^ 1ull);
-        }
+        else if (r.mode == 1) ctx->h_blk_shift[(size_t) (b0 + 5) * nchan] += 0x1p-51;
     }
     int64_t n = 0;
     for (int c = 0; c < nchan; c++) {
@@ -444,8 +461,11 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.nruns = ctx->nruns;
     a.run_samples = ctx->cfg.run_samples;
     a.iq16 = sample_size == GPSB200_SC16;
-    a.check_stride = 1;
-    a.check_phase = 0;
+    a.check_stride = ctx->check_stride;
+    a.check_phase = ctx->check_phase;
+    a.run_x = ctx->d_run_x + off * ctx->nruns * 2;
+    a.blk_shift = ctx->d_blk_shift + off;
+    a.blk_pick = ctx->d_blk_pick + off;
     // lanes per run follow the channel count; a CTA takes up to 24 warps' worth of runs
     const int grp = nchan > 16 ? 32 : (nchan > 8 ? 16 : 8);
     const int rpw = 32 / grp;
@@ -488,12 +508,12 @@ void drain(gpsb200_ctx *ctx, cudaStream_t extra) {
 // First part of a pipeline segment [b0, b1): host records + guesses, parameters up, carrier tables.
 int segment_params(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1, int nchan, int sample_size,
                    void *dst_dev, cudaStream_t sp, const std::vector<ChainState> &chain, gpsb200_stats_t &st,
-                   SynthArgs &a, gpsb200_slice_link_t *link) {
+                   SynthArgs &a, gpsb200_slice_link_t *link, std::vector<ChainState> *end_guess = nullptr) {
     const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
     const int nb = b1 - b0;
     const size_t off = (size_t) b0 * nchan, cnt = (size_t) nb * nchan;
     double t0 = now_ms();
-    int rc = prepare_blocks(ctx, chans, b0, b1, nchan, chain, link);
+    int rc = prepare_blocks(ctx, chans, b0, b1, nchan, chain, link, end_guess);
     if (rc) return rc;
     st.host_chain_ms += now_ms() - t0;
     CU(cudaMemcpyAsync(ctx->d_bc + off, ctx->h_bc + off, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, sp));
@@ -536,9 +556,11 @@ int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp
     if (first) CU(cudaEventRecord(ctx->ev[3], sp));
     CU(cudaMemcpyAsync(ctx->d_span_res + soff, ctx->h_span_res + soff, scnt * sizeof(SpanRes), cudaMemcpyHostToDevice, sp));
     st.h2d_bytes += (int64_t) (scnt * sizeof(SpanRes));
-    if (slow > 0) {                                  // rare: per-block start phases of the host-resolved spans
+    if (slow > 0) {                                  // rare: per-block resolutions of the host-resolved spans
         CU(cudaMemcpyAsync(ctx->d_carr0 + off, ctx->h_carr0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
-        st.h2d_bytes += (int64_t) (cnt * sizeof(double));
+        CU(cudaMemcpyAsync(ctx->d_blk_shift + off, ctx->h_blk_shift + off, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+        CU(cudaMemcpyAsync(ctx->d_blk_pick + off, ctx->h_blk_pick + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, sp));
+        st.h2d_bytes += (int64_t) (cnt * (2 * sizeof(double) + sizeof(int32_t)));
     }
     SynthArgs ack = a;
     ack.last_end_host = ctx->cur_seg < ctx->max_segs ? ctx->d_seg_end + (size_t) ctx->cur_seg * nchan : nullptr;
@@ -644,6 +666,7 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     gpsb200_stats_t st{};
     std::vector<ChainState> chain(nchan);
     seed_chain(chain, nchan, prn_in, phase_in);
+    ctx->check_phase = (ctx->check_phase + 1) % ctx->check_stride;      // the sampled exact re-walk rotates
     cudaStream_t sp = ctx->s_pre;                       // stream of the pre-phase
     CU(cudaEventRecord(ctx->ev[0], s));
     CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
@@ -652,7 +675,57 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     CU(cudaMemsetAsync(ctx->d_chain_errors, 0, sizeof(int), sp));
     int ichunk = 0, iseg = 0;
     const auto segs = segments_of(nblk);
+    if (!dst_host) {
+        // Device destination: nothing has to leave early, so everything speculative goes first -- the host prepares
+        // segment after segment (guesses continue from the GUESSED end of the previous segment) while the GPU already
+        // probes the earlier ones -- then the host scans the span summaries, and run checkpoints and synthesis are
+        // ONE launch each over the whole call.
+        std::vector<ChainState> guess = chain;
+        std::vector<SynthArgs> sa(segs.size());
+        for (size_t i = 0; i < segs.size(); i++) {
+            std::vector<ChainState> next(nchan);
+            rc = segment_params(ctx, chans, segs[i].first, segs[i].second, nchan, sample_size, dst_dev, sp, guess, st, sa[i], nullptr,
+                                &next);
+            if (rc) return rc;
+            rc = segment_probe(ctx, segs[i].first, segs[i].second, nchan, sp, st, i == 0, sa[i]);
+            if (rc) return rc;
+            CU(cudaEventRecord(ctx->ev_seg[std::min((int) i, ctx->max_segs - 1)], sp));
+            guess = next;
+        }
+        const double t0 = now_ms();
+        int64_t slow = 0;
+        for (size_t i = 0; i < segs.size(); i++) {
+            CU(cudaEventSynchronize(ctx->ev_seg[std::min((int) i, ctx->max_segs - 1)]));
+            int64_t reg = 0, sl = 0;
+            st.chain_fallbacks += (int32_t) resolve_chain(ctx, segs[i].first, segs[i].second, nchan, chain, &reg, &sl);
+            slow += sl;
+        }
+        st.host_chain_ms += now_ms() - t0;
+        SynthArgs all{};
+        fill_args(ctx, all, 0, nblk, nchan, sample_size, dst_dev);
+        const size_t cnt = (size_t) nblk * nchan, scnt = (size_t) all.nspan * nchan;
+        CU(cudaEventRecord(ctx->ev[3], sp));
+        CU(cudaMemcpyAsync(ctx->d_span_res, ctx->h_span_res, scnt * sizeof(SpanRes), cudaMemcpyHostToDevice, sp));
+        if (slow > 0) {
+            CU(cudaMemcpyAsync(ctx->d_carr0, ctx->h_carr0, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+            CU(cudaMemcpyAsync(ctx->d_blk_shift, ctx->h_blk_shift, cnt * sizeof(double), cudaMemcpyHostToDevice, sp));
+            CU(cudaMemcpyAsync(ctx->d_blk_pick, ctx->h_blk_pick, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, sp));
+        }
+        SynthArgs ack = all;
+        ack.last_end_host = ctx->d_seg_end;
+        CU(launch_checkpoints(ack, sp));
+        CU(cudaEventRecord(ctx->ev[4], sp));
+        rc = note_segment_end(ctx, 0, nblk, nchan, sp, chain);
+        if (rc) return rc;
+        iseg = 1;
+        CU(cudaEventRecord(ctx->ev_done[0], sp));
+        CU(cudaStreamWaitEvent(s, ctx->ev_done[0], 0));
+        CU(launch_synth(all, s));
+        st.launches += 2;
+        st.h2d_bytes += (int64_t) (scnt * sizeof(SpanRes));
+    }
     for (const auto &sg : segs) {
+        if (!dst_host) break;
         const int b0 = sg.first, b1 = sg.second;
         SynthArgs a{};
         rc = segment_params(ctx, chans, b0, b1, nchan, sample_size, dst_dev, sp, chain, st, a, nullptr);
@@ -921,6 +994,12 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_span_sum, nsc * sizeof(CarrierProbe), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void **) &ctx->d_span_sum, ctx->h_span_sum, 0));
     CU(cudaMalloc(&ctx->d_spec, nbc * sizeof(SpanBlockState)));
+    CU(cudaMalloc(&ctx->d_run_x, nbc * ctx->nruns * 2 * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_blk_shift, nbc * sizeof(double)));
+    CU(cudaHostAlloc(&ctx->h_blk_shift, nbc * sizeof(double), cudaHostAllocDefault));
+    CU(cudaMalloc(&ctx->d_blk_pick, nbc * sizeof(int32_t)));
+    CU(cudaHostAlloc(&ctx->h_blk_pick, nbc * sizeof(int32_t), cudaHostAllocDefault));
+    if (const char *ev = getenv("GPSB200_CHECK_STRIDE")) ctx->check_stride = std::max(1, atoi(ev));
     CU(cudaMalloc(&ctx->d_span_res, nsc * sizeof(SpanRes)));
     CU(cudaHostAlloc(&ctx->h_span_res, nsc * sizeof(SpanRes), cudaHostAllocDefault));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
@@ -963,6 +1042,11 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFree(ctx->d_probe);
     cudaFreeHost(ctx->h_span_sum);
     cudaFree(ctx->d_spec);
+    cudaFree(ctx->d_run_x);
+    cudaFree(ctx->d_blk_shift);
+    cudaFreeHost(ctx->h_blk_shift);
+    cudaFree(ctx->d_blk_pick);
+    cudaFreeHost(ctx->h_blk_pick);
     cudaFree(ctx->d_span_res);
     cudaFreeHost(ctx->h_span_res);
     cudaFree(ctx->d_nav);
@@ -1021,6 +1105,7 @@ int gpsb200_slice_prepare(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int n
     if (!link) return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_prepare: link is NULL");
     cudaStream_t s = stream_ ? (cudaStream_t) stream_ : ctx->s_compute;
     cudaStream_t sp = ctx->s_pre;
+    ctx->check_phase = (ctx->check_phase + 1) % ctx->check_stride;      // the sampled exact re-walk rotates
     CU(cudaEventRecord(ctx->ev[0], s));
     CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
     CU(cudaStreamWaitEvent(ctx->s_ck, ctx->ev[0], 0));

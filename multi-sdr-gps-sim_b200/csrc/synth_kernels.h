@@ -65,7 +65,13 @@ struct SynthArgs {
     int *chain_errors;        // self-check counter: blocks whose walked end phase != the next block's start phase
     void *out;                // nblk * 600000 int8 or int16
     int nblk, nchan, nruns, run_samples, runs_per_cta, ctas_per_block, iq16;
-    int check_stride, check_phase;   // k_checkpoints re-walks every block; the chain self-check compares all of them
+    // Run-start carrier states come from the block probes' trajectories (+ the resolved shift); every check_stride-th
+    // block (offset check_phase, rotating from call to call) and every block the host resolved by hand is ALSO walked
+    // exactly from its resolved start, and every run start and the end phase are compared (device self-check).
+    int check_stride, check_phase;
+    double *run_x;            // [nblk][nruns][nchan][2] run-start states of the block probes' variant trajectories
+    const double *blk_shift;  // [nblk][nchan] host-resolved spans (mode 1): shift of the block against its probe variant
+    const int32_t *blk_pick;  // [nblk][nchan] ... which variant; -1: the block has to be walked exactly
 };
 
 // Gain-scaled carrier tables of every block (gps.c:2781-2782), fetched by k_synth with TMA bulk copies.
