@@ -428,6 +428,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"k_probe_chain_ms": 0.0, "k_checkpoints_ms": 0.0, "k_synth_ms": 0.0, "host_chain_ms": 0.0}
     fallbacks = 0
+    launches = 0
     t_wall0 = time.time()
     ev0.record(stream)
     for i in range(args.steps):
@@ -435,6 +436,7 @@ def main():
         step_wait()                                           # the buffers are reused by the next step
         kern["host_chain_ms"] += st.host_chain_ms
         fallbacks += st.chain_fallbacks
+        launches += int(st.launches)
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
@@ -533,7 +535,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "f64 NCO / int32 accumulate / %s out" % ("int16" if args.iq16 else "int8"),
             "data": "synthetic", "config": workload_config(nchan, args.iq16, world, total_blocks, nblk),
-            "clocks": clocks, "gpu_launches": 6 * args.steps,
+            "clocks": clocks, "gpu_launches": launches,
             "timed_region": "per step the WHOLE path of the rank's slice: host records + guesses, 6 MB of parameters up, "
                             "carrier tables, block probes, span chaining, hand-over of the chain state (N > 1: NCCL "
                             "all-gather + send/recv), host scan, run checkpoints + self-check, synthesis into HBM",

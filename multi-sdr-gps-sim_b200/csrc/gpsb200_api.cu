@@ -138,6 +138,7 @@ struct gpsb200_ctx {
     double *d_run_x = nullptr;                         // run-start states of the block probes' variant trajectories
     double *d_blk_shift = nullptr, *h_blk_shift = nullptr;     // host-resolved spans: per-block shift / variant pick
     int32_t *d_blk_pick = nullptr, *h_blk_pick = nullptr;
+    int run_ld = 0;                                    // leading dimension (blocks, padded) of d_run_x
     int check_stride = 8, check_phase = 0;             // sampled exact re-walk of the chain (GPSB200_CHECK_STRIDE)
     SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
     int max_spans = 0, max_segs = 0;
@@ -146,7 +147,9 @@ struct gpsb200_ctx {
     std::vector<double> seg_expect;        // what the chain says they must be
     std::vector<cudaEvent_t> ev_seg;       // slice path: probes of segment i complete
     void *const *scatter = nullptr;        // gpsb200_synth_blocks_scatter: one host destination per block
-    bool fault_inject_chain = false;       // gpsb200_debug_corrupt_chain(): test hook of the device self-check
+    bool fault_inject_chain = false;
+    bool trace_on = false;
+    double trace_t0 = 0.0;       // gpsb200_debug_corrupt_chain(): test hook of the device self-check
     // state of a begun, not yet finished call (gpsb200_synth_begin / _finish)
     struct Pending {
         bool active = false;
@@ -177,6 +180,10 @@ struct OneSatellite {          // parameter accessor of span_chain() for the hos
     }
 };
 
+double now_ms();
+// GPSB200_TRACE=1: host time stamps of the pipeline's phases on stderr (diagnostics)
+void trace(gpsb200_ctx *ctx, const char *what);
+
 int fail(gpsb200_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
     return code;
@@ -192,6 +199,12 @@ int fail(gpsb200_ctx *c, int code, const std::string &msg) {
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void trace(gpsb200_ctx *ctx, const char *what) {
+    if (!ctx->trace_on) return;
+    const double t = now_ms();
+    fprintf(stderr, "[gpsb200 +%8.3f ms] %s\n", t - ctx->trace_t0, what);
 }
 
 // Host pre-pass: validate, fill the device-layout records and GUESS every block's start
@@ -463,7 +476,9 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.iq16 = sample_size == GPSB200_SC16;
     a.check_stride = ctx->check_stride;
     a.check_phase = ctx->check_phase;
-    a.run_x = ctx->d_run_x + off * ctx->nruns * 2;
+    a.run_x = ctx->d_run_x;
+    a.run_b0 = blk0;
+    a.run_ld = ctx->run_ld;
     a.blk_shift = ctx->d_blk_shift + off;
     a.blk_pick = ctx->d_blk_pick + off;
     // lanes per run follow the channel count; a CTA takes up to 24 warps' worth of runs
@@ -667,6 +682,8 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     std::vector<ChainState> chain(nchan);
     seed_chain(chain, nchan, prn_in, phase_in);
     ctx->check_phase = (ctx->check_phase + 1) % ctx->check_stride;      // the sampled exact re-walk rotates
+    ctx->trace_t0 = now_ms();
+    trace(ctx, "call");
     cudaStream_t sp = ctx->s_pre;                       // stream of the pre-phase
     CU(cudaEventRecord(ctx->ev[0], s));
     CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
@@ -682,25 +699,32 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
         // ONE launch each over the whole call.
         std::vector<ChainState> guess = chain;
         std::vector<SynthArgs> sa(segs.size());
+        CU(cudaStreamWaitEvent(ctx->s_ck, ctx->ev[0], 0));
         for (size_t i = 0; i < segs.size(); i++) {
+            // the segments' walk kernels alternate between two streams: their long tails (walk lengths differ by
+            // an order of magnitude between satellites) overlap instead of adding up
+            cudaStream_t sw = (i & 1) ? ctx->s_ck : sp;
             std::vector<ChainState> next(nchan);
-            rc = segment_params(ctx, chans, segs[i].first, segs[i].second, nchan, sample_size, dst_dev, sp, guess, st, sa[i], nullptr,
+            rc = segment_params(ctx, chans, segs[i].first, segs[i].second, nchan, sample_size, dst_dev, sw, guess, st, sa[i], nullptr,
                                 &next);
             if (rc) return rc;
-            rc = segment_probe(ctx, segs[i].first, segs[i].second, nchan, sp, st, i == 0, sa[i]);
+            rc = segment_probe(ctx, segs[i].first, segs[i].second, nchan, sw, st, i == 0, sa[i]);
             if (rc) return rc;
-            CU(cudaEventRecord(ctx->ev_seg[std::min((int) i, ctx->max_segs - 1)], sp));
+            CU(cudaEventRecord(ctx->ev_seg[std::min((int) i, ctx->max_segs - 1)], sw));
             guess = next;
         }
-        const double t0 = now_ms();
         int64_t slow = 0;
+        trace(ctx, "speculative work enqueued");
         for (size_t i = 0; i < segs.size(); i++) {
             CU(cudaEventSynchronize(ctx->ev_seg[std::min((int) i, ctx->max_segs - 1)]));
+            const double t0 = now_ms();
             int64_t reg = 0, sl = 0;
             st.chain_fallbacks += (int32_t) resolve_chain(ctx, segs[i].first, segs[i].second, nchan, chain, &reg, &sl);
             slow += sl;
+            st.host_chain_ms += now_ms() - t0;
         }
-        st.host_chain_ms += now_ms() - t0;
+        CU(cudaStreamSynchronize(ctx->s_ck));           // (its last segment's event has been waited for; this orders the
+        trace(ctx, "host scan done");                   //  checkpoint launch on sp behind everything on s_ck)
         SynthArgs all{};
         fill_args(ctx, all, 0, nblk, nchan, sample_size, dst_dev);
         const size_t cnt = (size_t) nblk * nchan, scnt = (size_t) all.nspan * nchan;
@@ -723,6 +747,7 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
         CU(launch_synth(all, s));
         st.launches += 2;
         st.h2d_bytes += (int64_t) (scnt * sizeof(SpanRes));
+        trace(ctx, "checkpoints + synthesis enqueued");
     }
     for (const auto &sg : segs) {
         if (!dst_host) break;
@@ -757,6 +782,7 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     // the device self-check of the carrier chain is never skipped: a wrong start phase must not produce samples silently
     CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sp));
     CU(cudaStreamSynchronize(sp));
+    trace(ctx, "pre-phase stream drained (self-check read)");
     rc = verify_chain(ctx, iseg, nchan);
     if (rc) return rc;
     if (dst_host) {
@@ -994,12 +1020,14 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_span_sum, nsc * sizeof(CarrierProbe), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void **) &ctx->d_span_sum, ctx->h_span_sum, 0));
     CU(cudaMalloc(&ctx->d_spec, nbc * sizeof(SpanBlockState)));
-    CU(cudaMalloc(&ctx->d_run_x, nbc * ctx->nruns * 2 * sizeof(double)));
+    ctx->run_ld = (c.max_blocks + 31) & ~31;
+    CU(cudaMalloc(&ctx->d_run_x, (size_t) ctx->run_ld * c.max_chan * ctx->nruns * 2 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_blk_shift, nbc * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_blk_shift, nbc * sizeof(double), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_blk_pick, nbc * sizeof(int32_t)));
     CU(cudaHostAlloc(&ctx->h_blk_pick, nbc * sizeof(int32_t), cudaHostAllocDefault));
     if (const char *ev = getenv("GPSB200_CHECK_STRIDE")) ctx->check_stride = std::max(1, atoi(ev));
+    if (const char *ev = getenv("GPSB200_TRACE")) ctx->trace_on = atoi(ev) != 0;
     CU(cudaMalloc(&ctx->d_span_res, nsc * sizeof(SpanRes)));
     CU(cudaHostAlloc(&ctx->h_span_res, nsc * sizeof(SpanRes), cudaHostAllocDefault));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
@@ -1149,16 +1177,20 @@ int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double 
     ctx->pending.st.host_chain_ms += now_ms() - t0;
     int rc = GPSB200_OK, iseg = 0;
     ctx->pending.eager = eager != 0;
-    for (const auto &sg : segments_of(nblk)) {          // speculative work: every segment now (eager), or the first
-        if (!ctx->pending.eager && iseg > 0) break;     // one only -- the others follow one by one in _finish
+    const auto segs = segments_of(nblk);
+    if (ctx->pending.eager) {
+        // everything speculative at once: ONE probe and ONE chaining launch over the whole slice (no per-segment tails)
         SynthArgs a{};
-        fill_args(ctx, a, sg.first, sg.second - sg.first, nchan, ctx->pending.sample_size, nullptr);
-        rc = segment_probe(ctx, sg.first, sg.second, nchan, ctx->s_pre, ctx->pending.st, sg.first == 0, a);
-        if (rc) break;
-        if (cudaEventRecord(ctx->ev_seg[iseg++], ctx->s_pre) != cudaSuccess) {
-            rc = fail(ctx, GPSB200_ERR_CUDA, "cudaEventRecord");
-            break;
-        }
+        fill_args(ctx, a, 0, nblk, nchan, ctx->pending.sample_size, nullptr);
+        rc = segment_probe(ctx, 0, nblk, nchan, ctx->s_pre, ctx->pending.st, true, a);
+        for (size_t i = 0; !rc && i < segs.size(); i++)
+            if (cudaEventRecord(ctx->ev_seg[i], ctx->s_pre) != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, "cudaEventRecord");
+    } else {
+        // only the first segment's; the others follow one by one in gpsb200_slice_finish
+        SynthArgs a{};
+        fill_args(ctx, a, segs[0].first, segs[0].second - segs[0].first, nchan, ctx->pending.sample_size, nullptr);
+        rc = segment_probe(ctx, segs[0].first, segs[0].second, nchan, ctx->s_pre, ctx->pending.st, true, a);
+        if (!rc && cudaEventRecord(ctx->ev_seg[iseg++], ctx->s_pre) != cudaSuccess) rc = fail(ctx, GPSB200_ERR_CUDA, "cudaEventRecord");
     }
     if (rc) {
         const std::string keep = ctx->err;

@@ -307,13 +307,12 @@ GPSB_HD void binade_margins(double v, double &m_pos, double &m_neg) {
 // jump, after the jump, after the real step) into them. Returns the number of steps done.
 // Degenerate increments (|c| < 2^-23) are not walked here: ok is cleared and the caller
 // treats the block as "no usable speculation".
-GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, bool &wrapped, bool &ok,
-                             double *m_pos, double *m_neg) {
+GPSB_HD int64_t carrier_walk_w(double &x, const WalkConst &w, int64_t n, bool stop_at_wrap, bool &wrapped, bool &ok,
+                               double *m_pos, double *m_neg) {
     wrapped = false;
     ok = true;
     if (n <= 0) return 0;
-    const WalkConst w = walk_const(c);
-    if (c == 0.0 || !w.fast) {
+    if (w.c == 0.0 || !w.fast) {
         ok = false;
         return 0;
     }
@@ -334,6 +333,12 @@ GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, 
         }
     }
     return (int64_t) (n0 - nd);
+}
+
+GPSB_HD int64_t carrier_walk(double &x, double c, int64_t n, bool stop_at_wrap, bool &wrapped, bool &ok,
+                             double *m_pos, double *m_neg) {
+    const WalkConst w = walk_const(c);
+    return carrier_walk_w(x, w, n, stop_at_wrap, wrapped, ok, m_pos, m_neg);
 }
 
 // One parity variant v of the probe (the device runs the two variants in different threads;
@@ -365,11 +370,12 @@ GPSB_HD void carrier_probe_variant(double guess, double c, int64_t n, int v, Car
     if (!(xv >= 0.0 && xv < 1.0)) mp = mn = 0.0;
     else if (run_samples <= 0 || !run_x) carrier_walk(xv, c, n - nw, false, w2, ok2, &mp, &mn);
     else {
+        const WalkConst wc = walk_const(c);
         int64_t pos = nw;
         int64_t r = (nw + run_samples - 1) / run_samples;         // first run that starts at or after the first wrap
         for (; pos < n; r++) {
             const int64_t stop = r * (int64_t) run_samples < n ? r * (int64_t) run_samples : n;
-            if (stop > pos) carrier_walk(xv, c, stop - pos, false, w2, ok2, &mp, &mn);
+            if (stop > pos) carrier_walk_w(xv, wc, stop - pos, false, w2, ok2, &mp, &mn);
             pos = stop;
             if (pos < n) run_x[(size_t) r * run_stride] = xv;
         }

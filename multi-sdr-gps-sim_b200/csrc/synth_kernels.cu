@@ -98,9 +98,9 @@ __global__ void __launch_bounds__(128) k_probe(SynthArgs a) {
     const BlockChanDev p = a.bc[i];
     CarrierProbe o;
     if (p.prn > 0) {
-        // run-start states of this variant's trajectory go to run_x[b][r][c][v]
-        double *rx = a.run_x ? a.run_x + (((size_t) b * a.nruns) * a.nchan + c) * 2 + v : nullptr;
-        carrier_probe_variant(a.guess[i], p.c_carr, kBlockSamples, v, o, a.run_samples, rx, (size_t) a.nchan * 2);
+        // run-start states of this variant's trajectory go to run_x[r][v][c][run_b0 + b]
+        double *rx = a.run_x ? a.run_x + ((size_t) v * a.nchan + c) * a.run_ld + a.run_b0 + b : nullptr;
+        carrier_probe_variant(a.guess[i], p.c_carr, kBlockSamples, v, o, a.run_samples, rx, (size_t) 2 * a.nchan * a.run_ld);
     } else {
         o.n_w = -1;
         o.x_w = 0.0;
@@ -224,14 +224,17 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
     }
     const CarrierProbe pr = a.probe[i];
     const bool derived = pick >= 0 && pr.n_w >= 0 && a.run_x != nullptr;
-    // the last block of a launch is always walked: its end phase is compared with the next launch's chain state
+    // Sampling is per WARP (= 32 consecutive blocks of one channel, see map_block_chan): a walked lane costs its whole
+    // warp the walk. The last block of a launch is always walked: its end phase is compared with the next launch's
+    // chain state.
     const bool check = !derived || by_hand || b == a.nblk - 1 || a.check_stride <= 1 ||
-                       ((b + a.check_phase) % a.check_stride) == 0;
+                       (((b >> 5) + a.check_phase) % a.check_stride) == 0;
     double x_end;
     if (derived) {
         // run starts before the probe's first wrap: exact walk from the resolved start (no wrap on the way, a handful
         // of iterations); from the first wrap on: the probe's trajectory plus the shift (exact, see nco_exact.h)
-        const double *rx = a.run_x + (((size_t) b * a.nruns) * a.nchan + c) * 2 + pick;
+        const double *rx = a.run_x + ((size_t) pick * a.nchan + c) * a.run_ld + a.run_b0 + b;
+        const size_t rstride = (size_t) 2 * a.nchan * a.run_ld;
         double x = start;
         int64_t pos = 0;
         for (int r = 0; r < a.nruns; r++) {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(128) k_checkpoints(SynthArgs a) {
                 pos = s_r;
                 v = x;
             } else {
-                v = rx[(size_t) r * a.nchan * 2] + shift;
+                v = rx[(size_t) r * rstride] + shift;
             }
             ck[(size_t) r * a.nchan].x = v;
         }

@@ -69,7 +69,10 @@ struct SynthArgs {
     // block (offset check_phase, rotating from call to call) and every block the host resolved by hand is ALSO walked
     // exactly from its resolved start, and every run start and the end phase are compared (device self-check).
     int check_stride, check_phase;
-    double *run_x;            // [nblk][nruns][nchan][2] run-start states of the block probes' variant trajectories
+    double *run_x;            // [nruns][2][nchan][run_ld] run-start states of the block probes' variant trajectories;
+                              // the block index is innermost (the walk kernels' warps are 32 consecutive blocks of one
+                              // channel: coalesced); indexed with the block number within the CONTEXT: run_b0 + b
+    int run_b0, run_ld;
     const double *blk_shift;  // [nblk][nchan] host-resolved spans (mode 1): shift of the block against its probe variant
     const int32_t *blk_pick;  // [nblk][nchan] ... which variant; -1: the block has to be walked exactly
 };
