@@ -1020,8 +1020,15 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_span_sum, nsc * sizeof(CarrierProbe), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer((void **) &ctx->d_span_sum, ctx->h_span_sum, 0));
     CU(cudaMalloc(&ctx->d_spec, nbc * sizeof(SpanBlockState)));
+    // Run-start carrier states taken from the probes' own trajectories (+ resolved shift) instead of a second exact
+    // walk: implemented and exact (GPU suite green with every block cross-checked), but measured on B200 it does not
+    // pay -- stopping the probe walks at the 125 run starts costs k_probe +0.75 ms per 2999 x 32 blocks, while
+    // k_checkpoints is bound by the latency of its longest walk, which sampling does not shorten. Off unless
+    // GPSB200_DERIVED_ANCHORS=1 (then every 8th warp of blocks, rotating, is still re-walked: GPSB200_CHECK_STRIDE).
     ctx->run_ld = (c.max_blocks + 31) & ~31;
-    CU(cudaMalloc(&ctx->d_run_x, (size_t) ctx->run_ld * c.max_chan * ctx->nruns * 2 * sizeof(double)));
+    if (const char *ev = getenv("GPSB200_DERIVED_ANCHORS"))
+        if (atoi(ev) != 0)
+            CU(cudaMalloc(&ctx->d_run_x, (size_t) ctx->run_ld * c.max_chan * ctx->nruns * 2 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_blk_shift, nbc * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_blk_shift, nbc * sizeof(double), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_blk_pick, nbc * sizeof(int32_t)));
