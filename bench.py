@@ -274,6 +274,7 @@ class HandOver:
             self.link_dev = torch.zeros(5 * 32, dtype=torch.float64, device="cuda")
             self.links_dev = torch.zeros(world * 5 * 32, dtype=torch.float64, device="cuda")
             self.state_dev = torch.zeros(64, dtype=torch.float64, device="cuda")
+            self.state_out = torch.zeros(64, dtype=torch.float64, device="cuda")
 
     def guessed_incoming(self, link):
         """all-gather of the links; -> (prn, phase) guessed state entering this rank's slice (None, None for rank 0)."""
@@ -298,7 +299,8 @@ class HandOver:
     def recv_exact(self):
         if self.rank == 0:
             return None, None
-        self.dist.recv(self.state_dev, src=self.rank - 1)
+        for w in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.irecv, self.state_dev, self.rank - 1)]):
+            w.wait()
         v = self.state_dev.cpu().numpy()
         return v[:32][:self.nchan].astype(self.np.int32), v[32:][:self.nchan].copy()
 
@@ -309,8 +311,9 @@ class HandOver:
         v = np.zeros(64)
         v[:self.nchan] = prn
         v[32:32 + self.nchan] = ph
-        self.state_dev.copy_(self.torch.from_numpy(v))
-        self.dist.send(self.state_dev, dst=self.rank + 1)
+        self.state_out.copy_(self.torch.from_numpy(v))
+        for w in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.isend, self.state_out, self.rank + 1)]):
+            w.wait()
 
 
 def main():
@@ -539,6 +542,8 @@ def main():
             "timed_region": "per step the WHOLE path of the rank's slice: host records + guesses, 6 MB of parameters up, "
                             "carrier tables, block probes, span chaining, hand-over of the chain state (N > 1: NCCL "
                             "all-gather + send/recv), host scan, run checkpoints + self-check, synthesis into HBM",
+            "value_kernels_only": round(samples_all / world / ((tb_ms + pr_ms + ck_ms + syn_ms) * 1e-3) / 1e6 * world, 1)
+            if world == 1 else None,
             "kernels": {"k_tables_ms": round(tb_ms, 3), "k_probe_chain_ms": round(pr_ms, 3), "k_checkpoints_ms": round(ck_ms, 3),
                         "k_synth_ms": round(syn_ms, 3), "host_chain_ms_per_step": round(kern["host_chain_ms"] / args.steps, 3),
                         "chain_fallback_blocks_per_step": fallbacks / args.steps,

@@ -275,8 +275,10 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 double g = (double) acc;
                 if (!(g >= 0.0 && g < 1.0)) g = 0.0;
                 ctx->h_guess[i] = g;
-                acc += (long double) GPSB200_BLOCK_SAMPLES *
-                       ((long double) o.c_carr + (long double) carrier_drift_per_step(o.c_carr));
+                // expected rounding drift: evaluated for every 4th block only and weighted accordingly -- the guesses
+                // need ~1e-9 cycles, the drift is ~3e-12 per block and only its running sum matters
+                const long double drift = (b & 3) == 0 ? 4.0L * (long double) carrier_drift_per_step(o.c_carr) : 0.0L;
+                acc += (long double) GPSB200_BLOCK_SAMPLES * ((long double) o.c_carr + drift);
                 acc -= floorl(acc);
             }
             if (end_guess) {
