@@ -350,7 +350,16 @@ def main():
     # the rank's threads and its page-locked result buffer go to the NUMA node of its GPU (library helper)
     numa_node = None if args.no_numa_bind else gps.bind_numa(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # high-priority NCCL streams: the hand-over messages are tiny kernels that must not wait behind walk kernels
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            opts = None
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+        except TypeError:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         torch.cuda.synchronize()
@@ -404,9 +413,10 @@ def main():
         gprn, gph = ho.guessed_incoming(link) if world > 1 else (None, None)
         ctx.slice_probe(gprn, gph, eager=rank + 1 < world)      # a successor waits for this slice's outgoing state
         prn_in, ph_in = ho.recv_exact() if world > 1 else (None, None)
-        prn_out, ph_out, st = ctx.slice_finish(prn_in, ph_in, want_stats=True)
-        if world > 1:
-            ho.send_exact(prn_out, ph_out)
+        # the exact outgoing state goes to the successor from inside the call, BEFORE the long kernels are enqueued (an
+        # NCCL send is a kernel too and would otherwise wait behind this rank's own synthesis)
+        prn_out, ph_out, st = ctx.slice_finish(prn_in, ph_in, want_stats=True,
+                                               handoff=ho.send_exact if rank + 1 < world else None)
         return st, ph_out
 
     # ---- value: the whole path, parameters in host memory (6 MB), result left in HBM ---------------------

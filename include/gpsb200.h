@@ -179,6 +179,12 @@ int gpsb200_slice_wait(gpsb200_ctx_t *ctx);
 int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_guess_in, int eager);
 int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
                          double *phase_out, gpsb200_stats_t *stats);
+/* Same with a hand-over callback: invoked with the exact outgoing state as soon as the host scan has it -- for an
+ * eager slice BEFORE the long kernels are enqueued, so that a message to the successor (an NCCL send is a kernel too)
+ * does not queue behind this slice's own synthesis. */
+typedef void (*gpsb200_handoff_fn)(void *user, const int32_t *prn_out, const double *phase_out);
+int gpsb200_slice_finish_cb(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
+                            double *phase_out, gpsb200_stats_t *stats, gpsb200_handoff_fn handoff, void *user);
 /* Host only: the link of a slice from its parameters alone (identical to what gpsb200_slice_prepare fills). */
 int gpsb200_slice_link_host(const gpsb200_chan_t *chans, int nblk, int nchan, gpsb200_slice_link_t *link);
 /* Host only: (prn_in, phase_in) -> guessed (prn_out, phase_out) after the slice `link` describes. */

@@ -67,13 +67,15 @@ class Stats(C.Structure):
                 ("chain_fallbacks", C.c_int32)]
 
 
+HANDOFF_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double))     # gpsb200_handoff_fn
+
 _lib = None
 
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_scatter", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
            "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_slice_prepare", "gpsb200_slice_probe",
-           "gpsb200_slice_finish", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
+           "gpsb200_slice_finish", "gpsb200_slice_finish_cb", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
            "gpsb200_scenario_chans", "gpsb200_scenario_nav",
@@ -118,6 +120,8 @@ def lib():
         L.gpsb200_span_chain_host.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.gpsb200_slice_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.POINTER(SliceLink)]
+        L.gpsb200_slice_finish_cb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats),
+                                              HANDOFF_FN, C.c_void_p]
         L.gpsb200_slice_wait.argtypes = [C.c_void_p]
         L.gpsb200_slice_link_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceLink)]
         L.gpsb200_slice_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -319,16 +323,23 @@ class Context:
         self._check(lib().gpsb200_slice_probe(self._h, None if pi is None else pi.ctypes.data,
                                               None if xi is None else xi.ctypes.data, 1 if eager else 0))
 
-    def slice_finish(self, prn_in=None, phase_in=None, want_stats=False):
-        """Step 3. -> (prn_out, phase_out[, Stats]): the exact chain state after the slice."""
+    def slice_finish(self, prn_in=None, phase_in=None, want_stats=False, handoff=None):
+        """Step 3. -> (prn_out, phase_out[, Stats]): the exact chain state after the slice. handoff(prn, phase), if
+        given, is called with that state as soon as the host scan has it -- for an eager slice before the long kernels
+        are enqueued (gpsb200_slice_finish_cb)."""
         n = self._slice_nchan
         pi = None if prn_in is None else np.ascontiguousarray(prn_in, dtype=np.int32)
         xi = None if phase_in is None else np.ascontiguousarray(phase_in, dtype=np.float64)
         po, xo = np.zeros(n, np.int32), np.zeros(n, np.float64)
         st = Stats()
-        self._check(lib().gpsb200_slice_finish(self._h, None if pi is None else pi.ctypes.data,
-                                               None if xi is None else xi.ctypes.data, po.ctypes.data, xo.ctypes.data,
-                                               C.byref(st)))
+
+        def _cb(_user, p_prn, p_ph):
+            handoff(np.ctypeslib.as_array(p_prn, shape=(n,)).copy(), np.ctypeslib.as_array(p_ph, shape=(n,)).copy())
+
+        cb = HANDOFF_FN(_cb) if handoff is not None else C.cast(None, HANDOFF_FN)
+        self._check(lib().gpsb200_slice_finish_cb(self._h, None if pi is None else pi.ctypes.data,
+                                                  None if xi is None else xi.ctypes.data, po.ctypes.data, xo.ctypes.data,
+                                                  C.byref(st), cb, None))
         return (po, xo, st) if want_stats else (po, xo)
 
     def slice_wait(self):

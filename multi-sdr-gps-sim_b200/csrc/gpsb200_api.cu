@@ -41,6 +41,9 @@ constexpr int kSegFirst = 256;     // first carrier-chain segment of the host-de
                                    // that the download can start early ...
 constexpr int kSegBlocks = 1024;   // ... later ones larger (their probe kernels are latency bound)
 constexpr int kSpanBlocks = 32;    // blocks per span of the two-level carrier chain (nco_exact.h: span_chain)
+constexpr int kHostChainBlocks = 2;   // calls of at most this many blocks (the reference's own cadence is ONE block per
+                                      // call, gps.c:2703-2865) skip the speculation: the host walks the few NCO chains
+                                      // exactly itself (~0.3 ms) instead of two latency-bound kernel round trips
 
 struct ChainState {
     int prn = 0;
@@ -122,7 +125,7 @@ struct gpsb200_ctx {
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> ev_done;      // one per synthesis chunk
     BlockChanDev *d_bc = nullptr, *h_bc = nullptr;
-    RunCkpt *d_ck = nullptr;
+    RunCkpt *d_ck = nullptr, *h_ck = nullptr;          // h_ck: run checkpoints of small calls, computed on the host
     uint32_t *d_nav = nullptr, *h_nav = nullptr;
     uint32_t *d_chips = nullptr;
     int32_t *d_atab = nullptr;             // per-block carrier tables (k_tables -> k_synth)
@@ -558,8 +561,12 @@ int segment_probe(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, 
 
 // Second half: wait for the span summaries, host scan from the chain state, resolutions up, exact run
 // checkpoints (+ device self-check). After it the segment's synthesis may be enqueued behind sp.
+int segment_checkpoints(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, gpsb200_stats_t &st, bool first,
+                        const SynthArgs &a, int64_t slow);
+
 int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, std::vector<ChainState> &chain,
-                    gpsb200_stats_t &st, bool first, const SynthArgs &a, cudaEvent_t probes_done = nullptr) {
+                    gpsb200_stats_t &st, bool first, const SynthArgs &a, cudaEvent_t probes_done = nullptr,
+                    int64_t *slow_out = nullptr) {
     // probes and span summaries must be in (mapped) host memory: wait for the segment's own probe event when the
     // post-scan work runs on a stream of its own (slice path), else for the pre-phase stream
     if (probes_done) CU(cudaEventSynchronize(probes_done));
@@ -568,6 +575,16 @@ int segment_resolve(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp
     int64_t reg = 0, slow = 0;
     st.chain_fallbacks += (int32_t) resolve_chain(ctx, b0, b1, nchan, chain, &reg, &slow);
     st.host_chain_ms += now_ms() - t0;
+    if (slow_out) {                 // scan only: the caller enqueues the device part later (segment_checkpoints)
+        *slow_out = slow;
+        return GPSB200_OK;
+    }
+    return segment_checkpoints(ctx, b0, b1, nchan, sp, st, first, a, slow);
+}
+
+// Device part of a segment's resolution: resolutions up, exact run checkpoints (+ self-check).
+int segment_checkpoints(gpsb200_ctx *ctx, int b0, int b1, int nchan, cudaStream_t sp, gpsb200_stats_t &st, bool first,
+                        const SynthArgs &a, int64_t slow) {
     const size_t off = (size_t) b0 * nchan, cnt = (size_t) (b1 - b0) * nchan;
     const size_t soff = (size_t) (b0 / kSpanBlocks) * nchan, scnt = (size_t) a.nspan * nchan;
     if (first) CU(cudaEventRecord(ctx->ev[3], sp));
@@ -631,6 +648,76 @@ void export_chain(const std::vector<ChainState> &chain, int nchan, int32_t *prn_
     }
 }
 
+// A call of one or two blocks (the reference's cadence): the host walks every NCO chain exactly (nco_exact.h) and
+// hands the device ready-made run checkpoints; tables + synthesis are the only kernels. Exact by construction.
+int small_call(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size, void *dst_dev,
+               void *dst_host, cudaStream_t s, std::vector<ChainState> &chain, int32_t *prn_out, double *carr_phase_out,
+               gpsb200_stats_t *stats) {
+    gpsb200_stats_t st{};
+    double t0 = now_ms();
+    int rc = prepare_blocks(ctx, chans, 0, nblk, nchan, chain);
+    if (rc) return rc;
+    const int nruns = ctx->nruns, run = ctx->cfg.run_samples;
+    ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
+        for (int c = c_lo; c < c_hi; c++) {
+            ChainState stc = chain[c];
+            for (int b = 0; b < nblk; b++) {
+                const BlockChanDev &p = ctx->h_bc[(size_t) b * nchan + c];
+                RunCkpt *ck = ctx->h_ck + (size_t) b * nruns * nchan + c;
+                if (p.prn <= 0) {
+                    stc.prn = 0;
+                    for (int r = 0; r < nruns; r++) ck[(size_t) r * nchan] = RunCkpt{0.0, 0.0, 0u, 0u};
+                    continue;
+                }
+                if (stc.prn != p.prn) stc.phase = p.carr_in;
+                stc.prn = p.prn;
+                double x = stc.phase, y = p.code0;
+                int iword = p.nav0 & 0xFF, ibit = (p.nav0 >> 8) & 0xFF, icode = (p.nav0 >> 16) & 0xFF;
+                for (int r = 0; r < nruns; r++) {
+                    ck[(size_t) r * nchan] = RunCkpt{x, y, (uint32_t) iword | ((uint32_t) ibit << 8) | ((uint32_t) icode << 16), 0u};
+                    int64_t periods = 0, dummy = 0;
+                    nco_advance<NCO_CARRIER>(x, p.c_carr, run, dummy);
+                    nco_advance<NCO_CODE>(y, p.c_code, run, periods);
+                    nav_advance(iword, ibit, icode, periods);
+                }
+                stc.phase = x;
+            }
+            chain[c] = stc;
+        }
+    });
+    st.host_chain_ms = now_ms() - t0;
+    rc = upload_nav(ctx, s);
+    if (rc) return rc;
+    const size_t cnt = (size_t) nblk * nchan;
+    CU(cudaEventRecord(ctx->ev[0], s));
+    CU(cudaMemcpyAsync(ctx->d_bc, ctx->h_bc, cnt * sizeof(BlockChanDev), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_ck, ctx->h_ck, cnt * nruns * sizeof(RunCkpt), cudaMemcpyHostToDevice, s));
+    SynthArgs a{};
+    fill_args(ctx, a, 0, nblk, nchan, sample_size, dst_dev);
+    CU(launch_tables(a, s));
+    CU(launch_synth(a, s));
+    CU(cudaEventRecord(ctx->ev[5], s));
+    st.launches = 2;
+    st.h2d_bytes = (int64_t) (cnt * (sizeof(BlockChanDev) + nruns * sizeof(RunCkpt)));
+    const size_t bytes = (size_t) nblk * GPSB200_BLOCK_ELEMS * sample_size;
+    if (dst_host) {
+        if (ctx->scatter) {
+            for (int b = 0; b < nblk; b++)
+                CU(cudaMemcpyAsync(ctx->scatter[b], (char *) dst_dev + (size_t) b * (bytes / nblk), bytes / nblk,
+                                   cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(cudaMemcpyAsync(dst_host, dst_dev, bytes, cudaMemcpyDeviceToHost, s));
+        }
+        st.d2h_bytes = (int64_t) bytes;
+        CU(cudaStreamSynchronize(s));
+    }
+    ctx->last = a;
+    ctx->have_last = false;              // nothing to replay: there were no walk kernels
+    export_chain(chain, nchan, prn_out, carr_phase_out);
+    if (stats) *stats = st;
+    return GPSB200_OK;
+}
+
 // Pipeline segments of a call: a short first one (its chain resolution is the lead-in of everything), then long ones.
 std::vector<std::pair<int, int>> segments_of(int nblk) {
     std::vector<std::pair<int, int>> v;
@@ -686,6 +773,8 @@ int run_pipeline_inner(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, 
     ctx->check_phase = (ctx->check_phase + 1) % ctx->check_stride;      // the sampled exact re-walk rotates
     ctx->trace_t0 = now_ms();
     trace(ctx, "call");
+    if (nblk <= kHostChainBlocks && !ctx->fault_inject_chain)
+        return small_call(ctx, chans, nblk, nchan, sample_size, dst_dev, dst_host, s, chain, prn_out, carr_phase_out, stats);
     cudaStream_t sp = ctx->s_pre;                       // stream of the pre-phase
     CU(cudaEventRecord(ctx->ev[0], s));
     CU(cudaStreamWaitEvent(sp, ctx->ev[0], 0));         // earlier work on s may still read the buffers rewritten now
@@ -1002,6 +1091,8 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaMalloc(&ctx->d_bc, nbc * sizeof(BlockChanDev)));
     CU(cudaHostAlloc(&ctx->h_bc, nbc * sizeof(BlockChanDev), cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_ck, nbc * ctx->nruns * sizeof(RunCkpt)));
+    CU(cudaHostAlloc(&ctx->h_ck, (size_t) std::min(c.max_blocks, kHostChainBlocks) * c.max_chan * ctx->nruns * sizeof(RunCkpt),
+                     cudaHostAllocDefault));
     CU(cudaMalloc(&ctx->d_carr_end, nbc * sizeof(double)));
     CU(cudaMalloc(&ctx->d_atab, (size_t) c.max_blocks * kAtabRows * 32 * sizeof(int32_t)));
     CU(cudaMalloc(&ctx->d_chain_errors, sizeof(int)));
@@ -1067,6 +1158,7 @@ void gpsb200_destroy(gpsb200_ctx_t *ctx) {
     cudaFree(ctx->d_bc);
     cudaFreeHost(ctx->h_bc);
     cudaFree(ctx->d_ck);
+    cudaFreeHost(ctx->h_ck);
     cudaFree(ctx->d_carr_end);
     cudaFree(ctx->d_atab);
     cudaFree(ctx->d_chain_errors);
@@ -1213,21 +1305,43 @@ int gpsb200_slice_probe(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double 
 }
 
 namespace {
-int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200_stats_t &st) {
+int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200_stats_t &st, int32_t *prn_out,
+                       double *phase_out, gpsb200_handoff_fn handoff, void *user) {
     const int nblk = ctx->pending.nblk, nchan = ctx->pending.nchan, sample_size = ctx->pending.sample_size;
     const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
     cudaStream_t s = ctx->pending.stream, sk = ctx->s_ck;
+    const auto segs = segments_of(nblk);
+    std::vector<int64_t> slow(segs.size(), 0);
+    std::vector<std::vector<ChainState>> after(segs.size());
+    if (ctx->pending.eager) {
+        // A successor waits for the outgoing state: scan EVERYTHING first (all probes were submitted up front), hand
+        // the exact state on, and only then enqueue the long kernels -- a message sent behind them would wait for them.
+        for (size_t i = 0; i < segs.size(); i++) {
+            SynthArgs a{};
+            int rc = segment_resolve(ctx, segs[i].first, segs[i].second, nchan, sk, chain, st, i == 0, a, ctx->ev_seg[i], &slow[i]);
+            if (rc) return rc;
+            after[i] = chain;
+        }
+        export_chain(chain, nchan, prn_out, phase_out);
+        if (handoff) handoff(user, prn_out, phase_out);
+    }
     int iseg = 0, ichunk = 0;
-    for (const auto &sg : segments_of(nblk)) {
-        const int b0 = sg.first, b1 = sg.second;
+    for (size_t i = 0; i < segs.size(); i++) {
+        const int b0 = segs[i].first, b1 = segs[i].second;
         SynthArgs a{};
         fill_args(ctx, a, b0, b1 - b0, nchan, sample_size, (char *) ctx->pending.dst + (size_t) b0 * blk_bytes);
-        // host scan of this segment as soon as ITS probes are done; checkpoints on a stream of their own, so that
-        // they do not queue behind the probes of later segments; the synthesis follows on the caller's stream
         ctx->cur_seg = iseg;
-        int rc = segment_resolve(ctx, b0, b1, nchan, sk, chain, st, b0 == 0, a, ctx->ev_seg[iseg]);
-        if (rc) return rc;
-        rc = note_segment_end(ctx, iseg++, b1, nchan, sk, chain);
+        int rc;
+        if (ctx->pending.eager) {
+            rc = segment_checkpoints(ctx, b0, b1, nchan, sk, st, b0 == 0, a, slow[i]);
+            if (rc) return rc;
+            rc = note_segment_end(ctx, iseg++, b1, nchan, sk, after[i]);
+        } else {
+            // lazy: host scan of this segment as soon as ITS probes are done; checkpoints on a stream of their own
+            rc = segment_resolve(ctx, b0, b1, nchan, sk, chain, st, b0 == 0, a, ctx->ev_seg[iseg]);
+            if (rc) return rc;
+            rc = note_segment_end(ctx, iseg++, b1, nchan, sk, chain);
+        }
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev_done[ichunk], sk));
         CU(cudaStreamWaitEvent(s, ctx->ev_done[ichunk], 0));
@@ -1240,8 +1354,8 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
             st.launches += 1;
         }
         if (!ctx->pending.eager && b1 < nblk) {
-            // lazy: the next segment's speculative work is submitted only now, BEHIND this segment's synthesis (it
-            // runs in its shadow), from guesses re-anchored on the exact state just resolved
+            // lazy: the next segment's speculative work is submitted only now, BEHIND this segment's synthesis, from
+            // guesses re-anchored on the exact state just resolved
             const int n1 = std::min(nblk, b1 + kSegBlocks);
             reanchor_guesses(ctx, b1, n1, nchan, chain);
             SynthArgs an{};
@@ -1251,6 +1365,10 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
             CU(cudaEventRecord(ctx->ev_seg[iseg], ctx->s_pre));
         }
     }
+    if (!ctx->pending.eager) {
+        export_chain(chain, nchan, prn_out, phase_out);
+        if (handoff) handoff(user, prn_out, phase_out);
+    }
     ctx->pending.nseg = iseg;
     CU(cudaEventRecord(ctx->ev[5], s));
     CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sk));
@@ -1258,8 +1376,8 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
 }
 }  // namespace
 
-int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
-                         double *phase_out, gpsb200_stats_t *stats) {
+int gpsb200_slice_finish_cb(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
+                            double *phase_out, gpsb200_stats_t *stats, gpsb200_handoff_fn handoff, void *user) {
     if (!ctx) return GPSB200_ERR_ARG;
     if (!ctx->pending.active || !ctx->pending.probed)
         return fail(ctx, GPSB200_ERR_ARG, "gpsb200_slice_finish: call gpsb200_slice_prepare and gpsb200_slice_probe first");
@@ -1269,7 +1387,9 @@ int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double
     std::vector<ChainState> chain(nchan);
     seed_chain(chain, nchan, prn_in, phase_in);
     gpsb200_stats_t st = ctx->pending.st;
-    const int rc = slice_finish_inner(ctx, chain, st);
+    std::vector<int32_t> po(nchan, 0);
+    std::vector<double> xo(nchan, 0.0);
+    const int rc = slice_finish_inner(ctx, chain, st, po.data(), xo.data(), handoff, user);
     if (rc) {
         const std::string keep = ctx->err;
         drain(ctx, ctx->pending.stream);
@@ -1281,9 +1401,17 @@ int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double
     ctx->last = all;
     ctx->have_last = true;
     ctx->pending.finished = true;
-    export_chain(chain, nchan, prn_out, phase_out);       // exact; the synthesis is still running: hand it on now
+    for (int c = 0; c < nchan; c++) {
+        if (prn_out) prn_out[c] = po[c];
+        if (phase_out) phase_out[c] = xo[c];
+    }
     if (stats) *stats = st;
     return GPSB200_OK;
+}
+
+int gpsb200_slice_finish(gpsb200_ctx_t *ctx, const int32_t *prn_in, const double *phase_in, int32_t *prn_out,
+                         double *phase_out, gpsb200_stats_t *stats) {
+    return gpsb200_slice_finish_cb(ctx, prn_in, phase_in, prn_out, phase_out, stats, nullptr, nullptr);
 }
 
 int gpsb200_slice_wait(gpsb200_ctx_t *ctx) {

@@ -423,7 +423,7 @@ def test_randomized_differential_vs_oracle():
     for case in range(40):
         nchan = int(rng.choice([1, 3, 8, 12, 16, 20, 32]))
         ss = int(rng.choice([1, 2]))
-        nblk = int(rng.choice([1, 2]))
+        nblk = int(rng.choice([1, 2, 3, 4]))             # 1-2: host-resolved small-call path, 3+: speculative chain
         ch, _ = gps.synthetic_chans(nblk, nchan, seed=1000 + case)
         nframes = 3
         nav = rng.integers(0, 1 << 32, size=(nframes, nchan, 60), dtype=np.uint32)   # incl. garbage in bits 30..31
@@ -558,7 +558,9 @@ def _three_step_slices(ch, nav, edges, sample_size=1):
             prn, ph = gps.link_apply(link, nchan, prn, ph)
         prn, ph, fallbacks = None, None, 0
         for ctx in ctxs:                                      # exact states, rank to rank
-            prn, ph, st = ctx.slice_finish(prn, ph, want_stats=True)
+            handed = []
+            prn, ph, st = ctx.slice_finish(prn, ph, want_stats=True, handoff=lambda a, b: handed.append((a, b)))
+            assert len(handed) == 1 and np.array_equal(handed[0][0], prn) and np.array_equal(handed[0][1], ph)
             fallbacks += st.chain_fallbacks
         for ctx in ctxs:
             ctx.slice_wait()                                  # completion + verdict of the device self-check

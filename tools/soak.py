@@ -3,11 +3,13 @@
 
   python tools/soak.py [--cases N] [--chains M] [--seed S]
 
-1. N one/two-block cases with parameters far outside a real constellation (the generator of
+1. N one- to four-block cases (1-2 blocks: the host-resolved small-call path; 3-4: block probes, span chaining and the
+   exact run checkpoints on the device) with parameters far outside a real constellation (the generator of
    tests/test_gpu_parity.py::test_randomized_differential_vs_oracle with fresh seeds): CUDA path
    vs the CPU oracle, bit for bit, samples and carried-out carrier phases.
-2. M long carrier chains (3000 blocks x 32 channels, random Doppler scale per chain): the
-   parallel-in-time device chain (probe kernel + host fix-up) vs the sequential exact host walk.
+2. M long carrier chains (3000 blocks x 32 channels, random Doppler scale per chain): the two-level
+   parallel-in-time device chain (block probes, span chaining, host scan over span summaries) vs the sequential exact
+   host walk.
 Prints one summary line per part; exit code 1 on the first mismatch."""
 import argparse
 import importlib
@@ -27,7 +29,7 @@ import scenario  # noqa: E402  (tests/scenario.py: oracle driver)
 def one_case(rng, case, seed):
     nchan = int(rng.choice([1, 3, 8, 12, 16, 20, 32]))
     ss = int(rng.choice([1, 2]))
-    nblk = int(rng.choice([1, 2]))
+    nblk = int(rng.choice([1, 2, 3, 4]))
     ch, _ = gps.synthetic_chans(nblk, nchan, seed=seed + case)
     nframes = 3
     nav = rng.integers(0, 1 << 32, size=(nframes, nchan, 60), dtype=np.uint32)
