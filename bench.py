@@ -350,6 +350,7 @@ def main():
     # the rank's threads and its page-locked result buffer go to the NUMA node of its GPU (library helper)
     numa_node = None if args.no_numa_bind else gps.bind_numa(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # no "NCCL version ..." banner on stdout: ONE JSON line
         # high-priority NCCL streams: the hand-over messages are tiny kernels that must not wait behind walk kernels
         opts = None
         try:
@@ -400,6 +401,7 @@ def main():
     sh = stream.cuda_stream
     assert sh != 0
     ho = HandOver(gps, world, rank, nchan)
+    step_trace = []       # BENCH_TRACE=1: per step [prepare, links all-gather, probe, recv exact, finish(+send)] ms, host share
 
     def one_step(dst_ptr=0, dst_host=None):
         """One pass of the whole hot path over this rank's slice: host records, parameters up, carrier tables, block
@@ -409,14 +411,24 @@ def main():
             # once everything is enqueued and the chain self-check of the whole call has been read)
             ph, st1 = ctx.synth_blocks_device(chans, ss, dst_ptr, stream=sh, want_stats=True)
             return st1, ph
+        tr = [time.perf_counter()]
         link = ctx.slice_prepare(chans, ss, dst_ptr, stream=sh, dst_host=dst_host)
+        tr.append(time.perf_counter())
         gprn, gph = ho.guessed_incoming(link) if world > 1 else (None, None)
-        ctx.slice_probe(gprn, gph, eager=rank + 1 < world)      # a successor waits for this slice's outgoing state
+        tr.append(time.perf_counter())
+        # eager on every rank of a multi-GPU run: a successor waits for the outgoing state, and the last rank has to wait
+        # for its incoming state anyway -- time in which all of its probes complete
+        ctx.slice_probe(gprn, gph, eager=world > 1)
+        tr.append(time.perf_counter())
         prn_in, ph_in = ho.recv_exact() if world > 1 else (None, None)
+        tr.append(time.perf_counter())
         # the exact outgoing state goes to the successor from inside the call, BEFORE the long kernels are enqueued (an
         # NCCL send is a kernel too and would otherwise wait behind this rank's own synthesis)
         prn_out, ph_out, st = ctx.slice_finish(prn_in, ph_in, want_stats=True,
                                                handoff=ho.send_exact if rank + 1 < world else None)
+        tr.append(time.perf_counter())
+        if os.environ.get("BENCH_TRACE"):
+            step_trace.append([round((b - a) * 1e3, 3) for a, b in zip(tr[:-1], tr[1:])] + [round(st.host_chain_ms, 3)])
         return st, ph_out
 
     # ---- value: the whole path, parameters in host memory (6 MB), result left in HBM ---------------------
@@ -455,6 +467,8 @@ def main():
     barrier()
     t_wall1 = time.time()
     total_ms = ev0.elapsed_time(ev1)
+    if os.environ.get("BENCH_TRACE") and step_trace:
+        note("step phases [prepare, links, probe, recv, finish+send | host_chain] ms: %s" % step_trace[-3:])
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps

@@ -133,6 +133,7 @@ struct gpsb200_ctx {
     int *d_chain_errors = nullptr, *h_chain_errors = nullptr;   // device self-check of the carrier chain
     double *d_guess = nullptr, *h_guess = nullptr;     // speculative block-start phases
     std::vector<uint8_t> h_guess_abs;                  // relative-mode marker per (block, channel), see prepare_blocks
+    std::vector<uint8_t> h_span_flags;                 // per (span, channel): 1 = every block idle, 2 = one satellite throughout
     double *d_carr0 = nullptr, *h_carr0 = nullptr;     // exact block-start phases of host-resolved (irregular) spans
     CarrierProbe *d_probe = nullptr;                   // block probes in HBM (k_chain reads them)
     CarrierProbe *h_probe = nullptr, *d_probe_host = nullptr;   // ... and in mapped host memory (host fallback)
@@ -207,11 +208,20 @@ double now_ms() {
 void trace(gpsb200_ctx *ctx, const char *what) {
     if (!ctx->trace_on) return;
     const double t = now_ms();
-    fprintf(stderr, "[gpsb200 +%8.3f ms] %s\n", t - ctx->trace_t0, what);
+    fprintf(stderr, "[gpsb200 dev %d +%8.3f ms] %s (%d host workers)\n", ctx->cfg.device, t - ctx->trace_t0, what,
+            ctx->pool ? ctx->pool->size() : 0);
 }
 
 // Host pre-pass: validate, fill the device-layout records and GUESS every block's start
 // carrier phase (closed form + expected rounding drift, long double accumulation).
+// Phases as 64-bit fixed point (cycles * 2^64, modulo one cycle) for the closed-form guesses.
+inline uint64_t phase_to_fix(double p) { return (p >= 0.0 && p < 1.0) ? (uint64_t) (p * 0x1p64) : 0; }
+inline double fix_to_phase(uint64_t a) { return (double) (a >> 11) * 0x1p-53; }
+inline uint64_t step_to_fix(double c) {     // c in (-1, 1): c * 2^64 modulo 2^64 (exact for |c| >= 2^-12, else truncated)
+    const uint64_t m = (uint64_t) (std::fabs(c) * 0x1p64);
+    return c < 0.0 ? (uint64_t) 0 - m : m;
+}
+
 // With link != NULL (time-slice hand-over, gpsb200_slice_prepare) the incoming chain state is not known yet:
 // guesses are accumulated RELATIVE to it (h_guess holds the advance since the slice start, h_guess_abs marks
 // blocks after a (re)allocation inside the slice, whose guesses are absolute) and finalize_guesses() adds the
@@ -225,20 +235,32 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
     std::vector<int> status(nchan, GPSB200_OK);
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
-            long double acc = chain[c].phase;               // exact phase after block b0-1 (if any)
+            // phase accumulator in cycles * 2^64, modulo 2^64 (= modulo one cycle): exact integer arithmetic
+            uint64_t acc = phase_to_fix(chain[c].phase);    // exact phase after block b0-1 (if any)
             int prev_prn = chain[c].prn;                    // 0 at the start of a call: block 0 is "fresh"
             bool absolute = link == nullptr;                // relative mode: true once a slot was (re)allocated
             if (link) {
-                acc = 0.0L;
+                acc = 0;
                 prev_prn = chans[(size_t) b0 * nchan + c].prn;      // block b0 continues whatever comes in (decided later)
                 link->prn_first[c] = prev_prn;
                 link->first_phase[c] = prev_prn > 0 ? chans[(size_t) b0 * nchan + c].carr_phase : 0.0;
             }
+            int span_first_prn = 0;
+            uint8_t span_idle = 1, span_uniform = 1;
             for (int b = b0; b < b1; b++) {
                 const gpsb200_chan_t &in = chans[(size_t) b * nchan + c];
                 const size_t i = (size_t) b * nchan + c;
                 BlockChanDev &o = ctx->h_bc[i];
                 memset(&o, 0, sizeof o);
+                // what the host scan wants to know about the span this block belongs to (resolve_chain)
+                if (b % kSpanBlocks == 0) {
+                    span_first_prn = in.prn;
+                    span_idle = span_uniform = 1;
+                }
+                span_idle &= in.prn <= 0;
+                span_uniform &= in.prn == span_first_prn;
+                if ((b + 1) % kSpanBlocks == 0 || b + 1 == b1)
+                    ctx->h_span_flags[(size_t) (b / kSpanBlocks) * nchan + c] = (uint8_t) (span_idle | (span_uniform << 1));
                 ctx->h_guess[i] = 0.0;
                 ctx->h_guess_abs[i] = absolute ? 1 : 0;
                 if (in.prn <= 0) {
@@ -262,7 +284,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                     return;
                 }
                 if (in.prn != prev_prn) {
-                    acc = in.carr_phase;
+                    acc = phase_to_fix(in.carr_phase);
                     absolute = true;
                 }
                 ctx->h_guess_abs[i] = absolute ? 1 : 0;
@@ -275,27 +297,22 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 o.prn = in.prn;
                 o.nav0 = (uint32_t) in.iword | ((uint32_t) in.ibit << 8) | ((uint32_t) in.icode << 16);
                 o.frame = in.nav_frame;
-                double g = (double) acc;
-                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
-                ctx->h_guess[i] = g;
-                // expected rounding drift: evaluated for every 4th block only and weighted accordingly -- the guesses
-                // need ~1e-9 cycles, the drift is ~3e-12 per block and only its running sum matters
-                const long double drift = (b & 3) == 0 ? 4.0L * (long double) carrier_drift_per_step(o.c_carr) : 0.0L;
-                acc += (long double) GPSB200_BLOCK_SAMPLES * ((long double) o.c_carr + drift);
-                acc -= floorl(acc);
+                ctx->h_guess[i] = fix_to_phase(acc);
+                // one block: 300000 steps of c, plus the expected rounding drift (evaluated for every 4th block only and
+                // weighted accordingly -- the guesses need ~1e-9 cycles, the drift is ~3e-12 per block and only its
+                // running sum matters)
+                acc += (uint64_t) GPSB200_BLOCK_SAMPLES * step_to_fix(o.c_carr);
+                if ((b & 3) == 0)
+                    acc += (uint64_t) (int64_t) (4.0 * (double) GPSB200_BLOCK_SAMPLES * carrier_drift_per_step(o.c_carr) * 0x1p64);
             }
             if (end_guess) {
-                double g = (double) acc;
-                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
                 (*end_guess)[c].prn = prev_prn > 0 ? prev_prn : 0;
-                (*end_guess)[c].phase = prev_prn > 0 ? g : 0.0;
+                (*end_guess)[c].phase = prev_prn > 0 ? fix_to_phase(acc) : 0.0;
             }
             if (link) {
                 link->prn_last[c] = prev_prn > 0 ? prev_prn : 0;
                 link->reset_inside[c] = absolute ? 1 : 0;
-                double g = (double) acc;
-                if (!(g >= 0.0 && g < 1.0)) g = 0.0;
-                link->value[c] = g;
+                link->value[c] = fix_to_phase(acc);
             }
         }
     });
@@ -397,12 +414,8 @@ int64_t resolve_chain(gpsb200_ctx *ctx, int b0, int b1, int nchan, std::vector<C
                 const int s0 = b0 + sp * K, s1 = std::min(b1, s0 + K);
                 SpanRes &res = ctx->h_span_res[(size_t) (s0 / K) * nchan + c];
                 const BlockChanDev &first = ctx->h_bc[(size_t) s0 * nchan + c];
-                bool idle = true, uniform = true;
-                for (int b = s0; b < s1; b++) {
-                    const int prn = ctx->h_bc[(size_t) b * nchan + c].prn;
-                    idle &= prn <= 0;
-                    uniform &= prn == first.prn;
-                }
+                const uint8_t flags = ctx->h_span_flags[(size_t) (s0 / K) * nchan + c];     // from prepare_blocks
+                const bool idle = flags & 1, uniform = flags & 2;
                 res.start = res.shift = 0.0;
                 res.variant = 0;
                 if (idle) {
@@ -1100,6 +1113,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaMalloc(&ctx->d_guess, nbc * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_guess, nbc * sizeof(double), cudaHostAllocDefault));
     ctx->h_guess_abs.assign(nbc, 1);
+    ctx->h_span_flags.assign((size_t) ((c.max_blocks + kSpanBlocks - 1) / kSpanBlocks + 1) * c.max_chan, 0);
     CU(cudaMalloc(&ctx->d_carr0, nbc * sizeof(double)));
     CU(cudaHostAlloc(&ctx->h_carr0, nbc * sizeof(double), cudaHostAllocDefault));
     // block probes: one copy in HBM (k_chain reads it), one written by the kernel straight into mapped
@@ -1313,17 +1327,25 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
     const auto segs = segments_of(nblk);
     std::vector<int64_t> slow(segs.size(), 0);
     std::vector<std::vector<ChainState>> after(segs.size());
+    ctx->trace_t0 = now_ms();
+    trace(ctx, "slice_finish");
     if (ctx->pending.eager) {
         // A successor waits for the outgoing state: scan EVERYTHING first (all probes were submitted up front), hand
         // the exact state on, and only then enqueue the long kernels -- a message sent behind them would wait for them.
         for (size_t i = 0; i < segs.size(); i++) {
             SynthArgs a{};
+            if (i == 0) {
+                CU(cudaEventSynchronize(ctx->ev_seg[0]));
+                trace(ctx, "probes complete");
+            }
             int rc = segment_resolve(ctx, segs[i].first, segs[i].second, nchan, sk, chain, st, i == 0, a, ctx->ev_seg[i], &slow[i]);
             if (rc) return rc;
             after[i] = chain;
         }
+        trace(ctx, "host scan done");
         export_chain(chain, nchan, prn_out, phase_out);
         if (handoff) handoff(user, prn_out, phase_out);
+        trace(ctx, "handed over");
     }
     int iseg = 0, ichunk = 0;
     for (size_t i = 0; i < segs.size(); i++) {
@@ -1372,6 +1394,7 @@ int slice_finish_inner(gpsb200_ctx *ctx, std::vector<ChainState> &chain, gpsb200
     ctx->pending.nseg = iseg;
     CU(cudaEventRecord(ctx->ev[5], s));
     CU(cudaMemcpyAsync(ctx->h_chain_errors, ctx->d_chain_errors, sizeof(int), cudaMemcpyDeviceToHost, sk));
+    trace(ctx, "checkpoints + synthesis enqueued");
     return GPSB200_OK;
 }
 }  // namespace

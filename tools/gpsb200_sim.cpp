@@ -241,7 +241,7 @@ int main(int argc, char **argv) {
                     gpsb200_slice_link_t link;
                     if (gpsb200_slice_prepare(ctx, chans + (size_t) lo[r] * nchan, nb, nchan, sample_size, nullptr, slice_host[r],
                                               nullptr, &link) != GPSB200_OK) break;
-                    if (gpsb200_slice_probe(ctx, r ? gprn[r].data() : nullptr, r ? gph[r].data() : nullptr, r + 1 < gpus) != GPSB200_OK) break;
+                    if (gpsb200_slice_probe(ctx, r ? gprn[r].data() : nullptr, r ? gph[r].data() : nullptr, 1) != GPSB200_OK) break;
                     const int32_t *pin = nullptr;
                     const double *xin = nullptr;
                     if (r > 0) {                                        // the exact state after slice r-1
