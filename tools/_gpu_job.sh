@@ -1,4 +1,6 @@
-mkdir -p gpurun_out/r2m
-nproc; cat /sys/fs/cgroup/cpu.max; cat /sys/fs/cgroup/cpuset.cpus.effective 2>/dev/null | head -2
-(GPSB200_TRACE=1 BENCH_TRACE=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 2 --warmup 1 --no-e2e > gpurun_out/r2m/bench_4gpu.json 2> gpurun_out/r2m/bench_4gpu.err)
-grep "gpsb200 dev\|step phases" gpurun_out/r2m/bench_4gpu.err | tail -44 | cut -c1-300
+mkdir -p gpurun_out/r2n
+(timeout 1800 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/r2n/tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2n/tests.log)
+(timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r2n/bench.json 2> gpurun_out/r2n/bench.err)
+tail -9 gpurun_out/r2n/tests.log; python -c "
+import json
+j=json.loads([l for l in open('gpurun_out/r2n/bench.json') if l.startswith('{')][-1]); print(j['value'], j['ms_per_step'], j.get('value_kernels_only'), j['kernels']); print(j['e2e'])"
