@@ -250,7 +250,7 @@ def workload_config(nchan, iq16, gpus, stream_blocks, per_rank_blocks):
             "channels": nchan, "stream_blocks": stream_blocks, "blocks_per_gpu": per_rank_blocks,
             "sample_format": "int16" if iq16 else "int8",
             "parallelism": "time-slice x%d; NCCL only for the hand-over of the slices' carrier-chain state "
-                           "(all-gather of closed-form links, exact phases rank to rank); no data-path collective" % gpus,
+                           "(guessed, then exact phases, rank to rank: send/recv); no data-path collective" % gpus,
             "l2": "output %.2f GB + checkpoints per rank and step >> 126 MB L2 (no flush needed)" % (
                 per_rank_blocks * 600000 * (2 if iq16 else 1) / 1e9)}
 
@@ -260,9 +260,9 @@ BLOCKS_3600S = 35999          # BASELINE configs[4]: -d 3600
 
 class HandOver:
     """The carrier-chain hand-over of a time-sliced stream over NCCL (include/gpsb200.h, "time-slice hand-over"):
-    every step, all ranks all-gather their slices' closed-form links (5 x 32 numbers) and compose them into GUESSED
-    incoming states; after the speculative GPU work the EXACT state (32 satellite ids + 32 phases) travels rank to
-    rank with send/recv. Nothing else crosses NVLink."""
+    every step two small messages (32 satellite ids + 32 phases each) travel rank to rank with send/recv -- first the
+    GUESSED state (closed-form links composed down the ranks, available before any GPU work), later the EXACT one.
+    Nothing else crosses NVLink."""
 
     def __init__(self, gps, world, rank, nchan):
         import numpy as np
@@ -271,29 +271,33 @@ class HandOver:
         self.gps, self.world, self.rank, self.nchan = gps, world, rank, nchan
         self.np, self.torch, self.dist = np, torch, dist
         if world > 1:
-            self.link_dev = torch.zeros(5 * 32, dtype=torch.float64, device="cuda")
-            self.links_dev = torch.zeros(world * 5 * 32, dtype=torch.float64, device="cuda")
+            self.guess_in = torch.zeros(64, dtype=torch.float64, device="cuda")
+            self.guess_out = torch.zeros(64, dtype=torch.float64, device="cuda")
             self.state_dev = torch.zeros(64, dtype=torch.float64, device="cuda")
             self.state_out = torch.zeros(64, dtype=torch.float64, device="cuda")
 
     def guessed_incoming(self, link):
-        """all-gather of the links; -> (prn, phase) guessed state entering this rank's slice (None, None for rank 0)."""
+        """The GUESSED state entering this rank's slice, passed down the ranks: receive the guess composed by the
+        predecessors, apply the own slice's closed-form link (gpsb200_link_apply), send the result on. Only ranks
+        r' < r matter to rank r, so nothing here makes an early rank wait for a late one: consecutive steps overlap
+        across ranks like the stages of a pipeline. -> (prn, phase), (None, None) for rank 0."""
         if self.world == 1:
             return None, None
-        np, torch, gps = self.np, self.torch, self.gps
-        flat = np.concatenate([np.asarray(link.prn_first, np.float64), np.asarray(link.prn_last, np.float64),
-                               np.asarray(link.reset_inside, np.float64), np.asarray(link.first_phase, np.float64),
-                               np.asarray(link.value, np.float64)])
-        self.link_dev.copy_(torch.from_numpy(flat))
-        self.dist.all_gather_into_tensor(self.links_dev, self.link_dev)
-        allv = self.links_dev.cpu().numpy().reshape(self.world, 5, 32)
+        np, gps = self.np, self.gps
         prn, ph = None, None
-        for q in range(self.rank):
-            lk = gps.SliceLink()
-            for c in range(32):
-                lk.prn_first[c], lk.prn_last[c], lk.reset_inside[c] = int(allv[q, 0, c]), int(allv[q, 1, c]), int(allv[q, 2, c])
-                lk.first_phase[c], lk.value[c] = float(allv[q, 3, c]), float(allv[q, 4, c])
-            prn, ph = gps.link_apply(lk, self.nchan, prn, ph)
+        if self.rank > 0:
+            for w in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.irecv, self.guess_in, self.rank - 1)]):
+                w.wait()
+            v = self.guess_in.cpu().numpy()
+            prn, ph = v[:32][:self.nchan].astype(np.int32), v[32:][:self.nchan].copy()
+        if self.rank + 1 < self.world:
+            pn, xn = gps.link_apply(link, self.nchan, prn, ph)
+            v = np.zeros(64)
+            v[:self.nchan] = pn
+            v[32:32 + self.nchan] = xn
+            self.guess_out.copy_(self.torch.from_numpy(v))
+            for w in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.isend, self.guess_out, self.rank + 1)]):
+                w.wait()
         return prn, ph
 
     def recv_exact(self):
@@ -390,7 +394,9 @@ def main():
     bytes_per_sample = 4 if args.iq16 else 2
     # this rank's slice of ONE continuous scenario; nothing about the blocks before it is precomputed
     chans, nav = gps.synthetic_chans(nblk, nchan, seed=2024, block0=lo)
-    host_threads = max(1, min(16, host_cpus() // max(1, world)))
+    # host workers per rank: the ranks' host phases are staggered (each rank scans when its predecessor has handed over),
+    # so a rank may use more than its even share of the CPUs
+    host_threads = max(2, min(16, host_cpus() // max(1, (world + 1) // 2)))
     ctx = gps.Context(nchan, max_nblk, device=local, max_nav_frames=1, host_threads=host_threads,
                       run_samples=args.run_samples)
     ctx.set_nav_frames(nav)
