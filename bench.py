@@ -336,6 +336,7 @@ def main():
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of the finished slices")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node (A/B)")
     ap.add_argument("--run-samples", type=int, default=0, help="device work unit (0 = library default)")
+    ap.add_argument("--depth", type=int, default=2, help="contexts used alternately by consecutive steps (1: no overlap)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -397,21 +398,33 @@ def main():
     # host workers per rank: the ranks' host phases are staggered (each rank scans when its predecessor has handed over),
     # so a rank may use more than its even share of the CPUs
     host_threads = max(2, min(16, host_cpus() // max(1, (world + 1) // 2)))
-    ctx = gps.Context(nchan, max_nblk, device=local, max_nav_frames=1, host_threads=host_threads,
-                      run_samples=args.run_samples)
-    ctx.set_nav_frames(nav)
-    out_dev = torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, device="cuda")
-    # a dedicated (non-default) stream: handle 0 would mean "the context's own stream" to the C ABI,
-    # and torch.cuda.Event only sees the stream it is recorded on
-    stream = torch.cuda.Stream()
+    # Double buffering (--depth 2): consecutive steps alternate between two contexts with their own streams and
+    # output buffers, so that the speculative pre-phase of step k+1 (host records, probes, span chaining) runs while
+    # step k is still being synthesized -- what a streaming producer of successive stream chunks does. A step is still
+    # ONE pass of the whole path over one batch; K steps are timed from a common start to the completion of the last.
+    depth = max(1, args.depth)
+    ctxs, outs, streams = [], [], []
+    for _ in range(depth):
+        c = gps.Context(nchan, max_nblk, device=local, max_nav_frames=1, host_threads=host_threads,
+                        run_samples=args.run_samples)
+        c.set_nav_frames(nav)
+        ctxs.append(c)
+        outs.append(torch.empty(nblk * gps.BLOCK_ELEMS, dtype=torch.int16 if args.iq16 else torch.int8, device="cuda"))
+        # dedicated (non-default) streams: handle 0 would mean "the context's own stream" to the C ABI
+        streams.append(torch.cuda.Stream())
+    ctx, out_dev, stream = ctxs[0], outs[0], streams[0]
     sh = stream.cuda_stream
     assert sh != 0
+    slot = [0]            # which context / stream / output buffer the next step uses
     ho = HandOver(gps, world, rank, nchan)
     step_trace = []       # BENCH_TRACE=1: per step [prepare, links all-gather, probe, recv exact, finish(+send)] ms, host share
 
     def one_step(dst_ptr=0, dst_host=None):
         """One pass of the whole hot path over this rank's slice: host records, parameters up, carrier tables, block
         probes, span chaining, hand-over, host scan, run checkpoints (+ self-check), synthesis. -> Stats"""
+        ctx, sh = ctxs[slot[0]], streams[slot[0]].cuda_stream
+        if dst_ptr == "slot":
+            dst_ptr = outs[slot[0]].data_ptr()
         if world == 1 and dst_host is None:
             # one GPU: the public device-destination call (the same steps, pipelined segment by segment; it returns
             # once everything is enqueued and the chain self-check of the whole call has been read)
@@ -439,21 +452,26 @@ def main():
 
     # ---- value: the whole path, parameters in host memory (6 MB), result left in HBM ---------------------
     note("value leg: first full pass")
-    def step_wait():
+    def step_wait(k=None):
+        """Wait for the step that last used context k (default: the current slot)."""
+        k = slot[0] if k is None else k
         if world == 1:
-            stream.synchronize()
+            streams[k].synchronize()
         else:
-            ctx.slice_wait()          # completion + verdict of the device self-check
+            ctxs[k].slice_wait()      # completion + verdict of the device self-check
 
-    st, _ = one_step(out_dev.data_ptr())
-    step_wait()
+    for k in range(depth):            # first full pass on every context
+        slot[0] = k
+        st, _ = one_step("slot")
+        step_wait()
+    slot[0] = 0
     sampler = None
     if rank == 0:
         uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
         sampler = ClockSampler(local, uuid)
     note("value leg: %d warm-up + %d timed steps" % (args.warmup, args.steps))
     for _ in range(args.warmup):
-        one_step(out_dev.data_ptr())
+        one_step("slot")
         step_wait()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -461,16 +479,28 @@ def main():
     fallbacks = 0
     launches = 0
     t_wall0 = time.time()
-    ev0.record(stream)
+    tstream = torch.cuda.Stream()      # timing events: the device is idle at ev0 (barrier) and at ev1 (synchronize)
+    ev0.record(tstream)
+    busy = [False] * depth
     for i in range(args.steps):
-        st, ph_last = one_step(out_dev.data_ptr())
-        step_wait()                                           # the buffers are reused by the next step
+        slot[0] = i % depth
+        if busy[slot[0]]:
+            step_wait()                                       # this context's previous step: its buffers are reused now
+        st, ph_last = one_step("slot")
+        busy[slot[0]] = True
         kern["host_chain_ms"] += st.host_chain_ms
         fallbacks += st.chain_fallbacks
         launches += int(st.launches)
-    ev1.record(stream)
+    for k in range(depth):
+        if busy[k]:
+            step_wait(k)
+    torch.cuda.synchronize()
+    ev1.record(tstream)
     torch.cuda.synchronize()
     barrier()
+    slot[0] = (args.steps - 1) % depth                        # the context of the last step: its state is replayed below
+    ctx, out_dev, stream = ctxs[slot[0]], outs[slot[0]], streams[slot[0]]
+    sh = stream.cuda_stream
     t_wall1 = time.time()
     total_ms = ev0.elapsed_time(ev1)
     if os.environ.get("BENCH_TRACE") and step_trace:
@@ -569,6 +599,7 @@ def main():
             "dtype": "f64 NCO / int32 accumulate / %s out" % ("int16" if args.iq16 else "int8"),
             "data": "synthetic", "config": workload_config(nchan, args.iq16, world, total_blocks, nblk),
             "clocks": clocks, "gpu_launches": launches,
+            "pipeline_depth": depth,
             "timed_region": "per step the WHOLE path of the rank's slice: host records + guesses, 6 MB of parameters up, "
                             "carrier tables, block probes, span chaining, hand-over of the chain state (N > 1: NCCL "
                             "all-gather + send/recv), host scan, run checkpoints + self-check, synthesis into HBM",
@@ -603,7 +634,8 @@ def main():
                               "%d blocks of the sky-%d static scenario, one producer thread (all the reference has)"
                               % (99 if nchan <= 12 else 49, 32 if nchan > 12 else 12)}
         print(json.dumps(line))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
