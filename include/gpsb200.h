@@ -79,11 +79,12 @@ typedef struct gpsb200_ctx gpsb200_ctx_t;
 /* Per-call statistics (filled when the pointer is not NULL). Times in milliseconds. */
 typedef struct gpsb200_stats {
     double host_chain_ms;      /* host share of the carrier chain: start-phase guesses + fix-up scan */
-    double h2d_ms, kernel_ms, d2h_ms;   /* kernel_ms: CUDA-event span of the call's stream; h2d_ms/d2h_ms reserved (0) */
+    double h2d_ms, kernel_ms, d2h_ms;   /* kernel_ms: CUDA-event span of the call's stream (host-destination calls only);
+                                           h2d_ms / d2h_ms: reserved, always 0 (transfers overlap the kernels) */
     double checkpoint_kernel_ms, synth_kernel_ms, probe_kernel_ms;
     int64_t h2d_bytes, d2h_bytes;
     int32_t launches;          /* kernels launched by this call */
-    int32_t chain_fallbacks;   /* blocks whose speculative carrier probe was rejected (exact sequential walk used) */
+    int32_t chain_fallbacks;   /* blocks the host had to walk sequentially (their block probe was unusable) */
 } gpsb200_stats_t;
 
 /* Threading: a context may be used by one thread at a time; different contexts (same or different devices)
@@ -127,10 +128,11 @@ int gpsb200_synth_blocks_scatter(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans
 
 /* Same, but the output stays in device memory (dst_device: device pointer with room for
  * nblk * 600000 elements) and the synthesis is only ENQUEUED on `stream` (a cudaStream_t,
- * 0 = the context's own stream) -- the caller synchronizes before reading dst_device. (The
- * call itself waits for the small carrier-probe round trip and, with the synthesis already enqueued,
- * for the device self-check of the carrier chain: a failed check returns GPSB200_ERR_INTERNAL.) Used for kernel-only
- * timing and for multi-GPU time-slice sharding where each rank fills a device buffer. */
+ * 0 = the context's own stream) -- the caller synchronizes before reading dst_device. The call itself returns when
+ * the speculative pre-phase (block probes, span chaining), the host scan and the run checkpoints are done and the
+ * device self-check of the carrier chain has been read (a failed check returns GPSB200_ERR_INTERNAL, and nothing of the
+ * call is left in flight); it never waits for the synthesis, with or without a stats request (stats then carry no
+ * synthesis time). Used for kernel-resident consumers and by bench.py's one-GPU value leg. */
 int gpsb200_synth_blocks_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                                 int sample_size, void *dst_device, void *stream,
                                 double *carr_phase_out, gpsb200_stats_t *stats);
