@@ -611,9 +611,9 @@ def main():
                         "note": "kernels replayed back to back on the last step's resident state, CUDA events on the launching stream"},
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         # ncu --set full (profiles/r1_ncu_metrics.csv): dram read+write of one 600-block int8
-                         # launch = 98.7 + 304.7 MB for 360 MB of algorithmic bytes; scaled to this launch
-                         "traffic": (int(alg_bytes * (98.7 + 304.7) / 360.0) if not args.iq16 else None),
+                         # ncu --set full (profiles/r2_ncu_metrics.csv): dram read+write of one 600-block int8
+                         # launch = 98.3 + 303.6 MB for 360 MB of algorithmic bytes; scaled to this launch
+                         "traffic": (int(alg_bytes * (98.34 + 303.58) / 360.0) if not args.iq16 else None),
                          "peak_source": peak_src,
                          "note": "path is issue-slot / shared-memory bound, not HBM bound; see DESIGN.md and profiles/"},
             "e2e": e2e if e2e is not None else {"value": None, "unit": "Msamples/s", "error": e2e_err or "skipped (--no-e2e)"},
