@@ -481,6 +481,7 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.span_res = ctx->d_span_res + (size_t) (blk0 / kSpanBlocks) * nchan;
     a.ck = ctx->d_ck + off * ctx->nruns;
     a.nav = ctx->d_nav;
+    a.nav_stride = ctx->cfg.max_chan;
     a.chipbits = ctx->d_chips;
     a.atab = ctx->d_atab + (size_t) blk0 * kAtabRows * 32;
     a.carr_end = ctx->d_carr_end + off;
@@ -518,9 +519,9 @@ int upload_nav(gpsb200_ctx *ctx, cudaStream_t s) {
 
 int check_call(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int nblk, int nchan, int sample_size, void *dst) {
     if (!ctx) return GPSB200_ERR_ARG;
-    if (!chans || !dst || nblk < 1 || nblk > ctx->cfg.max_blocks || nchan != ctx->cfg.max_chan ||
+    if (!chans || !dst || nblk < 1 || nblk > ctx->cfg.max_blocks || nchan < 1 || nchan > ctx->cfg.max_chan ||
         (sample_size != GPSB200_SC08 && sample_size != GPSB200_SC16))
-        return fail(ctx, GPSB200_ERR_ARG, "bad arguments (nchan must equal cfg.max_chan; 1 <= nblk <= cfg.max_blocks)");
+        return fail(ctx, GPSB200_ERR_ARG, "bad arguments (1 <= nchan <= cfg.max_chan; 1 <= nblk <= cfg.max_blocks)");
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
     if (ctx->pending.active) return fail(ctx, GPSB200_ERR_ARG, "a call begun with gpsb200_synth_begin has not been finished");
     CU(cudaSetDevice(ctx->cfg.device));     // the caller may be a thread that never selected the context's device
@@ -1514,7 +1515,7 @@ int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on) {
 
 int gpsb200_carrier_chain_device(gpsb200_ctx_t *ctx, const gpsb200_chan_t *chans, int nblk, int nchan,
                                  const double *phase_in, double *phase_out) {
-    if (!ctx || !chans || !phase_out || nblk < 0 || nchan != ctx->cfg.max_chan) return GPSB200_ERR_ARG;
+    if (!ctx || !chans || !phase_out || nblk < 0 || nchan < 1 || nchan > ctx->cfg.max_chan) return GPSB200_ERR_ARG;
     if (!ctx->s_compute) return fail(ctx, GPSB200_ERR_CUDA, "context has no CUDA device");
     if (ctx->pending.active) return fail(ctx, GPSB200_ERR_ARG, "a call begun with gpsb200_synth_begin has not been finished");
     CU(cudaSetDevice(ctx->cfg.device));

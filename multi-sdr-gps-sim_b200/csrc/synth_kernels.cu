@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) k_synth(SynthArgs a) {
         const int w = i / GROUP, c = i % GROUP;
         uint32_t v = 0;
         if (c < a.nchan && bc[c].prn > 0)
-            v = a.nav[((size_t) bc[c].frame * a.nchan + c) * kNavWords + w];
+            v = a.nav[((size_t) bc[c].frame * a.nav_stride + c) * kNavWords + w];
         sm.nav[w][c] = v;
     }
     {

@@ -56,7 +56,8 @@ struct SynthArgs {
     const SpanRes *span_res;  // [nspan][nchan] the host scan's resolution of every span
     int span_blocks, nspan;
     RunCkpt *ck;              // [nblk][nruns][nchan]
-    const uint32_t *nav;      // [frames][nchan][60]
+    const uint32_t *nav;      // [frames][nav_stride][60]: rows are the context's channel slots (cfg.max_chan >= nchan)
+    int nav_stride;
     const uint32_t *chipbits; // [33][33] packed C/A chips per PRN (bit n = ca[n mod 1023]), row 0 unused
     int32_t *atab;            // [nblk][513][32] gain-scaled carrier table per block: I + (Q << 16), column = lane
     double *carr_end;         // [nblk][nchan] carrier phase after the block

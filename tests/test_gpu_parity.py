@@ -697,3 +697,16 @@ def test_cli_multi_gpu_slices_write_the_reference_stream(tmp_path):
     subprocess.check_call(base + ["-d", "3", "-t", "1500.5,33.3,120.25", "-o", str(out)])
     s = np.fromfile(out, dtype=np.int8).reshape(-1, gps.BLOCK_ELEMS)
     assert [zlib.crc32(r.tobytes()) for r in s] == list(gt["crcs"][:, 0])
+
+
+def test_fewer_channels_than_the_context_was_created_for():
+    """nchan <= cfg.max_chan: a 32-slot context synthesizing 12-channel calls (NAV rows are indexed by the context's
+    slots) equals a 12-slot context."""
+    ch, nav = gps.synthetic_chans(5, 12, seed=515)
+    with gps.Context(12, 5) as ctx:
+        ctx.set_nav_frames(nav)
+        want, cp = ctx.synth_blocks(ch, 1)
+    with gps.Context(32, 8) as ctx:
+        ctx.set_nav_frames(nav)
+        got, cp2 = ctx.synth_blocks(ch, 1)
+    assert np.array_equal(got, want) and np.array_equal(cp, cp2)

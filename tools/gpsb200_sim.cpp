@@ -93,6 +93,8 @@ int main(int argc, char **argv) {
     }
     const int nblk = gpsb200_scenario_blocks(scn), nchan = gpsb200_scenario_channels(scn);
     const int nframes = gpsb200_scenario_nav_frames(scn);
+    fprintf(stderr, "gpsb200-sim: note: no almanac pages are generated -- the stream equals the reference's with its almanac "
+                    "disabled (the reference enables it by default and downloads one)\n");
     const gpsb200_chan_t *chans = gpsb200_scenario_chans(scn);
     const uint32_t *nav = gpsb200_scenario_nav(scn);
     const size_t blk_bytes = (size_t) GPSB200_BLOCK_ELEMS * sample_size;
