@@ -109,7 +109,7 @@ int gpsb200_bind_numa(int device);
 int gpsb200_set_nav(gpsb200_ctx_t *ctx, int frame, int chan, const uint32_t dwrd[GPSB200_NAV_WORDS]);
 
 /* Synthesize nblk consecutive 0.1 s blocks (replaces gps.c:2767-2857 nblk times).
- *   chans       [nblk][nchan], host memory
+ *   chans       [nblk][nchan], host memory; 1 <= nchan <= cfg.max_chan (slot c of a call is NAV row c of the context)
  *   sample_size GPSB200_SC08: dst is int8  I,Q interleaved, iq >> 4 with modulo-256 narrowing (gps.c:2844)
  *               GPSB200_SC16: dst is int16 I,Q interleaved (gps.c:2842)
  *   dst         host memory (pinned is faster), nblk * 600000 elements, block after block
