@@ -235,6 +235,13 @@ int gpsb200_carrier_probe_fixup(double start, double guess, double f_carr, int64
  * resolves the span block by block). For tests. */
 int gpsb200_span_chain_host(const double *f_carr, int nblk, double start_true, double start_guess, double *starts_out);
 
+/* Host model of the lane = sample synthesis kernel (csrc/synth_lanes.h) for ONE block: the same window / band / repair
+ * logic, executed on the CPU, int16 I/Q out. force bits: 1 = repair every sample's index, 2 = exact chip signs for every
+ * window, 4 = every repair walks exactly from the run anchor. counters[4] = fast samples, repaired samples, exactly
+ * rebuilt sign windows, exact walks. For tests (the algorithm against the oracle without a GPU); not a product path. */
+int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan, const uint32_t *nav, int run_samples, int force,
+                              int16_t *iq, double *carr_out, int64_t *counters);
+
 /* C/A code of prn (1..32) as 0/1 chips (codegen, gps.c:272-309). */
 int gpsb200_codegen(int prn, uint8_t ca[GPSB200_CA_LEN]);
 

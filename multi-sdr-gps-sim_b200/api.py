@@ -74,7 +74,7 @@ _lib = None
 EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_version", "gpsb200_set_nav",
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_scatter", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
-           "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_slice_prepare", "gpsb200_slice_probe",
+           "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_lanes_model_block", "gpsb200_slice_prepare", "gpsb200_slice_probe",
            "gpsb200_slice_finish", "gpsb200_slice_finish_cb", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
@@ -163,6 +163,23 @@ def carrier_chain(chans, phase_in=None, threads=16):
     if rc:
         raise GpsB200Error(rc, "gpsb200_carrier_chain")
     return out
+
+
+def lanes_model_block(chans_row, nav_frame, run_samples=2400, force=0):
+    """Host model of the lane = sample kernel for one block. chans_row: CHAN_DTYPE[nchan]; nav_frame: uint32[nchan, 60].
+    -> (iq int16[600000], carr_out float64[nchan], counters int64[4])"""
+    a = np.ascontiguousarray(chans_row, dtype=CHAN_DTYPE)
+    nv = np.ascontiguousarray(nav_frame, dtype=np.uint32)
+    iq = np.zeros(BLOCK_ELEMS, np.int16)
+    co = np.zeros(a.size, np.float64)
+    cnt = np.zeros(4, np.int64)
+    L = lib()
+    L.gpsb200_lanes_model_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.gpsb200_lanes_model_block(a.ctypes.data, a.size, nv.ctypes.data, run_samples, force, iq.ctypes.data, co.ctypes.data,
+                                     cnt.ctypes.data)
+    if rc:
+        raise GpsB200Error(rc, "gpsb200_lanes_model_block")
+    return iq, co, cnt
 
 
 def span_chain_host(f_carr, start_true, start_guess):

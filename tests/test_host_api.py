@@ -258,3 +258,42 @@ def test_span_level_chain_is_exact_or_rejected():
     # a Doppler zero crossing inside the span changes the rounding grid: never accepted
     f = np.linspace(3.0, -3.0, 8) * 200.0
     assert gps.span_chain_host(f, 0.3, 0.3) is None
+
+
+def _lanes_case(nchan, seed, force=0, scale=1.0, edge=False):
+    ch, nav = gps.synthetic_chans(1, nchan, seed=seed)
+    ch["f_carr"] *= scale
+    ch["f_code"] = 1.023e6 + ch["f_carr"] / 1540.0
+    rng = np.random.default_rng(seed)
+    if edge:
+        e = rng.integers(0, 4, size=nchan)
+        ch["code_phase"][:, e == 1] = np.nextafter(1023.0, 0)
+        ch["code_phase"][:, e == 2] = 0.0
+        ch["icode"][:, e == 3] = 19
+        ch["ibit"][:, e == 3] = 29
+        ch["iword"][:, e == 3] = rng.integers(0, 59)
+        ch["carr_phase"][0] = rng.choice([0.0, np.nextafter(1.0, 0), 0.5, 2.0 ** -40], size=nchan)
+        ch["prn"][:, rng.random(nchan) < 0.15] = 0
+    want, carr = scenario.oracle_run(ch, nav, 2)
+    iq, carr_out, counters = gps.lanes_model_block(ch[0], nav[0], force=force)
+    return np.array_equal(iq, want), counters
+
+
+@pytest.mark.parametrize("nchan", [1, 5, 12, 16])
+def test_lane_per_sample_model_is_bit_exact(nchan):
+    """synth_lanes.h (fixed-point linear phases certified from exact anchors, residue-class chip words, band repair)
+    against the oracle's FP64 recurrences (gps.c:2767-2857), one block."""
+    for seed in (100, 101):
+        ok, counters = _lanes_case(nchan, seed)
+        assert ok, (nchan, seed, counters)
+        assert counters[0] > 299000                               # nearly every sample takes the integer-only path
+
+
+def test_lane_per_sample_model_extremes_and_forced_repairs():
+    """Doppler x6 / x1e-5, phases on the wrap, NAV bit edges, idle channels; and every repair path forced on."""
+    for seed, scale in ((300, 6.0), (301, 0.01), (302, 1e-5), (303, 2.5)):
+        ok, counters = _lanes_case(12, seed, 0, scale, edge=True)
+        assert ok, (seed, scale, counters)
+    for force in (1, 2, 3, 5, 7):
+        ok, counters = _lanes_case(8, 555, force, 1.0, edge=True)
+        assert ok, (force, counters)
