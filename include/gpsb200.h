@@ -197,6 +197,11 @@ int gpsb200_link_apply(const gpsb200_slice_link_t *link, int nchan, const int32_
  * rounding grid (on != 0); every synth call must then fail with GPSB200_ERR_INTERNAL instead of returning samples. */
 int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on);
 
+/* Name of the synthesis kernel a call with nchan channels launches on this context as it stands: "k_synth_lanes"
+ * (lane = sample: run length a multiple of 96, every code rate seen so far within 1.0002 .. 1.0302 MHz, 16-byte aligned
+ * destination, GPSB200_LANES != 0) or "k_synth" (lane = channel, no such conditions). Both are bit-exact; for reporting. */
+const char *gpsb200_synth_kernel_name(const gpsb200_ctx_t *ctx, int nchan);
+
 /* Re-run the device part of the previous gpsb200_synth_blocks_device call (parameters,
  * start phases and guesses already resident in HBM): used by bench.py to time the kernels
  * alone. kernel_mask bits: 8 = carrier tables, 4 = carrier probe, 1 = run checkpoints, 2 = synthesis. */
@@ -237,7 +242,8 @@ int gpsb200_span_chain_host(const double *f_carr, int nblk, double start_true, d
 
 /* Host model of the lane = sample synthesis kernel (csrc/synth_lanes.h) for ONE block: the same window / band / repair
  * logic, executed on the CPU, int16 I/Q out. force bits: 1 = repair every sample's index, 2 = exact chip signs for every
- * window, 4 = every repair walks exactly from the run anchor. counters[4] = fast samples, repaired samples, exactly
+ * window, 4 = every repair walks exactly from the run anchor, 8 = carry points of every window by the FP64 second
+ * opinion instead of the 32-bit estimate. counters[4] = fast samples, repaired samples, exactly
  * rebuilt sign windows, exact walks. For tests (the algorithm against the oracle without a GPU); not a product path. */
 int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan, const uint32_t *nav, int run_samples, int force,
                               int16_t *iq, double *carr_out, int64_t *counters);

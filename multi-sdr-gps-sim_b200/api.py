@@ -75,7 +75,7 @@ EXPORTS = ["gpsb200_create", "gpsb200_destroy", "gpsb200_last_error", "gpsb200_v
            "gpsb200_synth_blocks", "gpsb200_synth_blocks_scatter", "gpsb200_synth_blocks_device", "gpsb200_replay_device",
            "gpsb200_carrier_advance", "gpsb200_carrier_chain", "gpsb200_carrier_chain_device", "gpsb200_carrier_probe_fixup",
            "gpsb200_codegen", "gpsb200_bind_numa", "gpsb200_span_chain_host", "gpsb200_lanes_model_block", "gpsb200_slice_prepare", "gpsb200_slice_probe",
-           "gpsb200_slice_finish", "gpsb200_slice_finish_cb", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain",
+           "gpsb200_slice_finish", "gpsb200_slice_finish_cb", "gpsb200_slice_wait", "gpsb200_link_apply", "gpsb200_slice_link_host", "gpsb200_debug_corrupt_chain", "gpsb200_synth_kernel_name",
            "gpsb200_scenario_create", "gpsb200_scenario_destroy", "gpsb200_scenario_error",
            "gpsb200_scenario_blocks", "gpsb200_scenario_channels", "gpsb200_scenario_nav_frames",
            "gpsb200_scenario_chans", "gpsb200_scenario_nav",
@@ -128,6 +128,8 @@ def lib():
         L.gpsb200_slice_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         L.gpsb200_link_apply.argtypes = [C.POINTER(SliceLink), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gpsb200_debug_corrupt_chain.argtypes = [C.c_void_p, C.c_int]
+        L.gpsb200_synth_kernel_name.argtypes = [C.c_void_p, C.c_int]
+        L.gpsb200_synth_kernel_name.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -361,6 +363,9 @@ class Context:
 
     def slice_wait(self):
         self._check(lib().gpsb200_slice_wait(self._h))
+
+    def synth_kernel_name(self, nchan):
+        return lib().gpsb200_synth_kernel_name(self._h, int(nchan)).decode()
 
     def debug_corrupt_chain(self, on):
         self._check(lib().gpsb200_debug_corrupt_chain(self._h, 1 if on else 0))

@@ -30,6 +30,7 @@
 #include "../../include/gpsb200.h"
 #include "nco_exact.h"
 #include "synth_kernels.h"
+#include "synth_lanes.h"
 #include "synth_tables.h"
 
 using namespace gpsb200;
@@ -143,6 +144,8 @@ struct gpsb200_ctx {
     double *d_blk_shift = nullptr, *h_blk_shift = nullptr;     // host-resolved spans: per-block shift / variant pick
     int32_t *d_blk_pick = nullptr, *h_blk_pick = nullptr;
     int run_ld = 0;                                    // leading dimension (blocks, padded) of d_run_x
+    bool lanes_on = true;                              // GPSB200_LANES=0: always k_synth (lane = channel)
+    bool lanes_veto = false;                           // a channel record outside k_synth_lanes' range was seen
     int check_stride = 8, check_phase = 0;             // sampled exact re-walk of the chain (GPSB200_CHECK_STRIDE)
     SpanRes *d_span_res = nullptr, *h_span_res = nullptr;
     int max_spans = 0, max_segs = 0;
@@ -233,6 +236,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                    std::vector<ChainState> *end_guess = nullptr) {
     const double delt = 1.0 / (double) GPSB200_SAMPLERATE;     // gps.c:2298
     std::vector<int> status(nchan, GPSB200_OK);
+    std::vector<uint8_t> lanes_bad(nchan, 0);
     ctx->pool->run(nchan, [&](int c_lo, int c_hi) {
         for (int c = c_lo; c < c_hi; c++) {
             // phase accumulator in cycles * 2^64, modulo 2^64 (= modulo one cycle): exact integer arithmetic
@@ -291,6 +295,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
                 prev_prn = in.prn;
                 o.c_carr = in.f_carr * delt;                    // gps.c:2821
                 o.c_code = in.f_code * delt;                    // gps.c:2789
+                if (!lanes::code_step_ok(o.c_code) || !(std::fabs(o.c_carr) < 0.5)) lanes_bad[c] = 1;
                 o.gain = in.gain;
                 o.carr_in = in.carr_phase;
                 o.code0 = in.code_phase;
@@ -317,6 +322,10 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
     });
     for (int c = 0; c < nchan; c++)
         if (status[c] != GPSB200_OK) return fail(ctx, status[c], "invalid channel parameters in slot " + std::to_string(c));
+    // k_synth_lanes covers every code rate a GPS receiver can see (1.0002 .. 1.0302 MHz); anything else keeps this
+    // context on k_synth from here on (both are exact; the choice is sticky so that no launch mixes assumptions)
+    for (int c = 0; c < nchan; c++)
+        if (lanes_bad[c]) ctx->lanes_veto = true;
     // The reference stores (short)i_acc (gps.c:2834); the packed I/Q accumulation is
     // exact as long as |acc| stays inside int16, which bounds the sum of amplitudes.
     for (int b = b0; b < b1; b++) {
@@ -499,6 +508,7 @@ void fill_args(gpsb200_ctx *ctx, SynthArgs &a, int blk0, int nblk, int nchan, in
     a.run_ld = ctx->run_ld;
     a.blk_shift = ctx->d_blk_shift + off;
     a.blk_pick = ctx->d_blk_pick + off;
+    a.lanes = ctx->lanes_on && !ctx->lanes_veto ? 1 : 0;
     // lanes per run follow the channel count; a CTA takes up to 24 warps' worth of runs
     const int grp = nchan > 16 ? 32 : (nchan > 8 ? 16 : 8);
     const int rpw = 32 / grp;
@@ -1142,6 +1152,7 @@ int gpsb200_create(const gpsb200_config_t *cfg, gpsb200_ctx_t **out) {
     CU(cudaHostAlloc(&ctx->h_blk_pick, nbc * sizeof(int32_t), cudaHostAllocDefault));
     if (const char *ev = getenv("GPSB200_CHECK_STRIDE")) ctx->check_stride = std::max(1, atoi(ev));
     if (const char *ev = getenv("GPSB200_TRACE")) ctx->trace_on = atoi(ev) != 0;
+    if (const char *ev = getenv("GPSB200_LANES")) ctx->lanes_on = atoi(ev) != 0;
     CU(cudaMalloc(&ctx->d_span_res, nsc * sizeof(SpanRes)));
     CU(cudaHostAlloc(&ctx->h_span_res, nsc * sizeof(SpanRes), cudaHostAllocDefault));
     const size_t navb = (size_t) c.max_nav_frames * c.max_chan * GPSB200_NAV_WORDS * 4;
@@ -1505,6 +1516,15 @@ int gpsb200_link_apply(const gpsb200_slice_link_t *link, int nchan, const int32_
         phase_out[c] = (ph >= 0.0 && ph < 1.0) ? ph : 0.0;
     }
     return GPSB200_OK;
+}
+
+const char *gpsb200_synth_kernel_name(const gpsb200_ctx_t *ctx, int nchan) {
+    if (!ctx) return "";
+    SynthArgs a{};
+    a.nchan = nchan;
+    a.run_samples = ctx->cfg.run_samples;
+    a.lanes = ctx->lanes_on && !ctx->lanes_veto ? 1 : 0;
+    return synth_lanes_applicable(a) ? "k_synth_lanes" : "k_synth";
 }
 
 int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on) {

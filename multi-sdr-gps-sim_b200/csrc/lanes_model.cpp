@@ -57,12 +57,14 @@ extern "C" int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan,
         icode[c] = chans[c].icode;
     }
     std::vector<lanes::ChanRun> st(nchan);
+    std::vector<lanes::Anchor> an(nchan);
     for (int r = 0; r < nruns; r++) {
         for (int c = 0; c < nchan; c++) {
             const uint32_t *nv = nav + (size_t) c * 60;
             auto navf = [nv](int iw) { return nv[iw]; };
             const uint32_t pos = (uint32_t) iword[c] | ((uint32_t) ibit[c] << 8) | ((uint32_t) icode[c] << 16);
-            lanes::init_run(st[c], chans[c].prn > 0, x[c], y[c], pos, chans[c].f_carr * delt, chans[c].f_code * delt, navf);
+            an[c] = lanes::Anchor{x[c], y[c], chans[c].f_carr * delt, chans[c].f_code * delt, pos};
+            lanes::init_run(st[c], chans[c].prn > 0, x[c], y[c], pos, an[c].c, an[c].d, navf);
         }
         for (int w = 0; w < nwin; w++) {
             std::vector<uint32_t> S(3 * nchan, 0), base(nchan, 0), step(nchan, 0);
@@ -72,9 +74,9 @@ extern "C" int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan,
                 auto navf = [nv](int iw) { return nv[iw]; };
                 const uint32_t *cw = chipw[c].data();
                 auto chipf = [cw](int i) { return cw[i]; };
-                const bool ok = lanes::window_signs(st[c], chipf, navf, &S[3 * c]);
+                const bool ok = lanes::window_signs(st[c], chipf, navf, &S[3 * c], (force & 8) != 0);
                 if (!ok || (force & 2)) {
-                    lanes::exact_signs(st[c], w, chipf, navf, &S[3 * c]);
+                    lanes::exact_signs(an[c], w, chipf, navf, &S[3 * c]);
                     ++cnt[2];
                 }
                 base[c] = lanes::fast_base(st[c]);
@@ -92,7 +94,7 @@ extern "C" int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan,
                         const uint64_t m = st[c].P + (uint64_t) n * st[c].D;
                         const uint64_t frac = m & ((1ull << 55) - 1);
                         if ((force & 4) || frac < lanes::kBandCarr || frac > (1ull << 55) - lanes::kBandCarr) ++cnt[3];
-                        k = lanes::exact_index(st[c], w, n, (force & 4) != 0);
+                        k = lanes::exact_index(st[c].P, st[c].D, an[c], w, n, (force & 4) != 0);
                         repaired = true;
                     }
                     const int sign = (int) ((S[3 * c + rr] >> q) & 1u);

@@ -556,6 +556,7 @@ static cudaError_t launch_synth_t(const SynthArgs &a, cudaStream_t s) {
 }
 
 cudaError_t launch_synth(const SynthArgs &a, cudaStream_t s) {
+    if (synth_lanes_applicable(a)) return launch_synth_lanes(a, s);
     switch (group_for(a.nchan)) {
         case 32: return launch_synth_t<32>(a, s);
         case 16: return launch_synth_t<16>(a, s);
@@ -564,6 +565,7 @@ cudaError_t launch_synth(const SynthArgs &a, cudaStream_t s) {
 }
 
 void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *smem) {
+    if (synth_lanes_applicable(a)) return synth_lanes_launch_shape(a, ctas, threads, smem);
     const int grp = group_for(a.nchan), rpw = 32 / grp;
     *ctas = a.nblk * a.ctas_per_block;
     *threads = ((a.runs_per_cta + rpw - 1) / rpw) * 32;

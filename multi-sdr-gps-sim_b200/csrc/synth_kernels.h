@@ -74,6 +74,7 @@ struct SynthArgs {
                               // the block index is innermost (the walk kernels' warps are 32 consecutive blocks of one
                               // channel: coalesced); indexed with the block number within the CONTEXT: run_b0 + b
     int run_b0, run_ld;
+    int lanes;                // nonzero: calls of at most 16 channels may use k_synth_lanes (every code step in its range)
     const double *blk_shift;  // [nblk][nchan] host-resolved spans (mode 1): shift of the block against its probe variant
     const int32_t *blk_pick;  // [nblk][nchan] ... which variant; -1: the block has to be walked exactly
 };
@@ -88,6 +89,10 @@ cudaError_t launch_chain(const SynthArgs &a, cudaStream_t s);
 cudaError_t launch_checkpoints(const SynthArgs &a, cudaStream_t s);
 // The per-sample synthesis (gps.c:2767-2857): lanes = channels, warp-sum over channels.
 cudaError_t launch_synth(const SynthArgs &a, cudaStream_t s);
+// The lane = sample variant for at most 16 channels (synth_lanes.cu); launch_synth() dispatches to it when applicable.
+bool synth_lanes_applicable(const SynthArgs &a);
+cudaError_t launch_synth_lanes(const SynthArgs &a, cudaStream_t s);
+void synth_lanes_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *smem);
 // Threads per CTA and dynamic shared memory the synthesis launch will use (for reporting).
 void synth_launch_shape(const SynthArgs &a, int *ctas, int *threads, size_t *smem);
 

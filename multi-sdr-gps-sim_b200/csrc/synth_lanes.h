@@ -36,8 +36,9 @@ constexpr uint64_t kBandCode = 1ull << 22;         // 2^-32 chips
 constexpr uint64_t kBandCarr = 1ull << 23;         // 2^-41 cycles (units of 2^-64)
 constexpr uint32_t kBandFast = 128;                // units of 2^-32 cycles: slack of the 32-bit per-window phases
 
-// f_code range the residue-class construction needs: 0 < delta3 = 3 * c_code - 1 < 1/33 (at most one carry per class)
-GPSB_HD bool code_step_ok(double c_code) { return c_code > 0.33340 && c_code < 0.34340; }
+// f_code range the residue-class construction needs: 2^-6 <= delta3 = 3 * c_code - 1 < 1/33 (at most one carry per class
+// word; the carry point below 64): 1.0157 .. 1.0302 MHz at 3 Msps. GPS L1 C/A is 1.023 MHz +- a few Hz.
+GPSB_HD bool code_step_ok(double c_code) { return c_code >= 0.33855 && c_code < 0.34340; }
 
 // carrier phase in [0,1) -> cycles * 2^64 (truncated below 2^-64)
 GPSB_HD uint64_t carr_fix(double x) { return (x >= 0.0 && x < 1.0) ? (uint64_t) (x * 0x1p64) : 0; }
@@ -61,13 +62,15 @@ GPSB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {               // (
 struct ChanRun {
     uint64_t P, D;          // carrier: linear phase at the current window start, increment per sample
     uint64_t Y, E;          // code: linear phase at the current window start (chips * 2^54, < 1023 * 2^54), increment
-    double rinv;            // 1 / delta3 (delta3 in code fixed point)
-    double tband;           // band of the carry-point test, in units of q
+    uint32_t inv32;         // floor(2^79 / delta3), delta3 = 3 E - 2^54 in [2^48, 2^49): the carry-point division as a multiply
     int iword, ibit, icode, dbit;
-    // the exact anchor (for the repair paths)
-    double x0, y0, c, d;
-    int iword0, ibit0, icode0;
     bool active;
+};
+
+// The exact NCO state at the run start (RunCkpt) and the increments: what the repair paths walk from.
+struct Anchor {
+    double x0, y0, c, d;
+    uint32_t navpos;        // iword | ibit << 8 | icode << 16
 };
 
 template <class NavFn>
@@ -79,29 +82,62 @@ GPSB_HD int nav_bit_at(NavFn nav, int iw, int ib) {
 template <class NavFn>
 GPSB_HD void init_run(ChanRun &s, bool active, double x, double y, uint32_t navpos, double c, double d, NavFn nav) {
     s.active = active;
-    s.x0 = x;
-    s.y0 = y;
-    s.c = c;
-    s.d = d;
-    s.iword = s.iword0 = (int) (navpos & 0xFF);
-    s.ibit = s.ibit0 = (int) ((navpos >> 8) & 0xFF);
-    s.icode = s.icode0 = (int) ((navpos >> 16) & 0xFF);
+    s.iword = (int) (navpos & 0xFF);
+    s.ibit = (int) ((navpos >> 8) & 0xFF);
+    s.icode = (int) ((navpos >> 16) & 0xFF);
     s.P = carr_fix(x);
     s.D = carr_step_fix(c);
     s.Y = code_fix(y);
     s.E = code_fix(d);
     const uint64_t d3 = 3 * s.E - kOne54;
-    s.rinv = active ? 1.0 / (double) d3 : 0.0;
-    s.tband = (double) kBandCode * s.rinv + 0x1p-40;
+    s.inv32 = active ? (uint32_t) (0x1p79 / (double) d3) : 0u;                // in (2^30, 2^31]
     s.dbit = active ? nav_bit_at(nav, s.iword, s.ibit) : 0;
+}
+
+GPSB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t) (((uint64_t) a * b) >> 32);
+#endif
+}
+
+// Second opinion on the carry points of a window, in FP64: used when the 32-bit estimate of window_signs() lands within
+// its own error of an integer. c_lo / c_hi: the 64 chip-sign bits from chip j0 on. Returns false when a sample's linear
+// code phase is within the band of a chip boundary or a carry point stays ambiguous.
+GPSB_HD bool window_signs_fp64(const ChanRun &s, uint32_t c_lo, uint32_t c_hi, int j0, uint32_t S[3]) {
+    const uint64_t d3 = 3 * s.E - kOne54;
+    const double rinv = 1.0 / (double) d3;
+    const double tband = (double) kBandCode * rinv + 0x1p-40;                // band of the carry-point test, in units of q
+    bool certain = true;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const uint64_t phi = s.Y + (uint64_t) r * s.E;
+        const int J = (int) (phi >> 54) - j0;                                 // 0 or 1
+        const uint64_t F = phi & (kOne54 - 1);
+        // carry point: smallest q with F + q * d3 >= 1 chip. FP64 is exact enough OUTSIDE the band tested below:
+        // (1 - F) / d3 is at most 2^-45 off, the band is >= 2^-40.
+        const double t = (double) (kOne54 - F) * rinv;
+        const double tf = t < 64.0 ? (double) (int) t : 64.0;                 // floor (t > 0)
+        const int qs = (int) tf + 1;
+        certain &= F >= kBandCode;
+        if (qs <= 32) certain &= (t - tf >= tband) & (tf + 1.0 - t >= tband);
+        const uint32_t lowm = qs >= 32 ? 0xFFFFFFFFu : ((1u << qs) - 1u);
+        const uint32_t a = funnel_r(c_lo, c_hi, J), b = funnel_r(c_lo, c_hi, J + 1);
+        S[r] = (a & lowm) | (b & ~lowm);
+    }
+    return certain;
 }
 
 // The chip-sign words of the current window: S[r] bit q = sign flag (chip XOR data bit) of sample 3q + r.
 // chips(w) = word w of the channel's packed, periodically extended C/A code (bit n = ca[n mod 1023]).
 // Returns false when some sample's linear code phase is too close to a chip boundary (or the carry point of a class is
 // ambiguous): the caller then builds the words with exact_signs().
+// Integer arithmetic only on the common path: the carry point t = (1 chip - F) / delta3 of a class is estimated as
+// mulhi32((2^54 - F) >> 22, inv32) = t * 2^25, short of the true value by less than 2^-23 (three truncations); when its
+// fraction keeps 2^-21 away from 0 and 1 the floor is certain and so is the band condition (band <= 2^-26).
 template <class ChipFn, class NavFn>
-GPSB_HD bool window_signs(const ChanRun &s, ChipFn chips, NavFn nav, uint32_t S[3]) {
+GPSB_HD bool window_signs(const ChanRun &s, ChipFn chips, NavFn nav, uint32_t S[3], bool force_fp64 = false) {
     const int j0 = (int) (s.Y >> 54);
     // 64 chips from chip j0 on, data bit folded in; chips of the NEXT code period (position >= 1023 - j0) take the
     // next NAV bit when this period is the 20th of its bit (gps.c:2793-2812)
@@ -128,26 +164,22 @@ GPSB_HD bool window_signs(const ChanRun &s, ChipFn chips, NavFn nav, uint32_t S[
             }
         }
     }
-    const uint64_t d3 = 3 * s.E - kOne54;
-    bool certain = true;
+    bool certain = !force_fp64;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         const uint64_t phi = s.Y + (uint64_t) r * s.E;
         const int J = (int) (phi >> 54) - j0;                                 // 0 or 1
         const uint64_t F = phi & (kOne54 - 1);
-        // carry point: smallest q with F + q * d3 >= 1 chip. FP64 is exact enough OUTSIDE the band tested below:
-        // (1 - F) / d3 is at most 2^-45 off, the band is >= 2^-40.
-        const double t = (double) (kOne54 - F) * s.rinv;
-        const double tf = t < 64.0 ? (double) (int) t : 64.0;                 // floor (t > 0)
-        const int qs = (int) tf + 1;
-        certain &= F >= kBandCode;
-        if (qs <= 32) certain &= (t - tf >= s.tband) & (tf + 1.0 - t >= s.tband);
-        const uint32_t lowm = qs >= 32 ? 0xFFFFFFFFu : ((1u << qs) - 1u);
+        const uint32_t t25 = mulhi32((uint32_t) ((kOne54 - F) >> 22), s.inv32);   // F == 0 wraps to 0: uncertain below
+        const uint32_t fl = t25 >> 25, fr = t25 & ((1u << 25) - 1u);
+        certain &= (F >> 22) != 0;                                            // F >= kBandCode
+        certain &= (fl >= 32u) | ((fr >= 16u) & (fr < (1u << 25) - 16u));
+        const uint32_t lowm = fl >= 31u ? 0xFFFFFFFFu : ((2u << fl) - 1u);    // samples q < fl + 1 precede the carry
         const uint32_t a = funnel_r(c_lo, c_hi, J), b = funnel_r(c_lo, c_hi, J + 1);
         S[r] = (a & lowm) | (b & ~lowm);
-        (void) d3;
     }
-    return certain;
+    if (certain) return true;
+    return window_signs_fp64(s, c_lo, c_hi, j0, S);
 }
 
 // Next window: 96 samples on.
@@ -172,11 +204,11 @@ GPSB_HD void advance_window(ChanRun &s, NavFn nav) {
 // Exact chip-sign words of window w of the run (repair path): the reference's own code recurrence, stepped sample by
 // sample from the exact state at the window start (nco_exact.h).
 template <class ChipFn, class NavFn>
-GPSB_HD void exact_signs(const ChanRun &s, int w, ChipFn chips, NavFn nav, uint32_t S[3]) {
-    double y = s.y0;
-    int iword = s.iword0, ibit = s.ibit0, icode = s.icode0;
+GPSB_HD void exact_signs(const Anchor &an, int w, ChipFn chips, NavFn nav, uint32_t S[3]) {
+    double y = an.y0;
+    int iword = (int) (an.navpos & 0xFF), ibit = (int) ((an.navpos >> 8) & 0xFF), icode = (int) ((an.navpos >> 16) & 0xFF);
     int64_t periods = 0;
-    nco_advance<NCO_CODE>(y, s.d, (int64_t) w * kWindow, periods);
+    nco_advance<NCO_CODE>(y, an.d, (int64_t) w * kWindow, periods);
     nav_advance(iword, ibit, icode, periods);
     int dbit = nav_bit_at(nav, iword, ibit);
     S[0] = S[1] = S[2] = 0;
@@ -187,7 +219,7 @@ GPSB_HD void exact_signs(const ChanRun &s, int w, ChipFn chips, NavFn nav, uint3
         const int q = n / 3, r = n - 3 * q;
         S[r] |= flag << q;
         int64_t p = 0;
-        nco_step<NCO_CODE>(y, s.d, p);
+        nco_step<NCO_CODE>(y, an.d, p);
         if (p) {
             if (++icode >= 20) {
                 icode = 0;
@@ -201,15 +233,16 @@ GPSB_HD void exact_signs(const ChanRun &s, int w, ChipFn chips, NavFn nav, uint3
     }
 }
 
-// Carrier table index of sample n of the current window, certain by construction: 64-bit linear phase, and the exact
-// walk from the run anchor when that lies inside the band (w = window number within the run).
-GPSB_HD int exact_index(const ChanRun &s, int w, int n, bool force_walk = false) {
-    const uint64_t m = s.P + (uint64_t) n * s.D;
+// Carrier table index of sample n of a window whose linear start phase is P (increment D), certain by construction:
+// 64-bit linear phase, and the exact walk from the run anchor when that lies inside the band (w = window number within
+// the run).
+GPSB_HD int exact_index(uint64_t P, uint64_t D, const Anchor &an, int w, int n, bool force_walk = false) {
+    const uint64_t m = P + (uint64_t) n * D;
     const uint64_t frac = m & ((1ull << 55) - 1);
     if (!force_walk && frac >= kBandCarr && frac <= (1ull << 55) - kBandCarr) return (int) (m >> 55);
-    double x = s.x0;
+    double x = an.x0;
     int64_t dummy = 0;
-    nco_advance<NCO_CARRIER>(x, s.c, (int64_t) w * kWindow + n, dummy);
+    nco_advance<NCO_CARRIER>(x, an.c, (int64_t) w * kWindow + n, dummy);
 #if defined(__CUDA_ARCH__)
     return __double2loint(__dadd_rz(x, 8796093022208.0)) & 511;              // (int) floor(x * 512), gps.c:2775
 #else

@@ -710,3 +710,34 @@ def test_fewer_channels_than_the_context_was_created_for():
         ctx.set_nav_frames(nav)
         got, cp2 = ctx.synth_blocks(ch, 1)
     assert np.array_equal(got, want) and np.array_equal(cp, cp2)
+
+
+@pytest.mark.parametrize("nchan,ss", [(1, 1), (5, 2), (8, 1), (12, 1), (12, 2), (16, 2), (17, 1), (23, 2), (32, 1), (32, 2)])
+def test_both_synthesis_kernels(nchan, ss, monkeypatch):
+    """k_synth_lanes (lane = sample; the 16- and the 32-channel variant) is the default; GPSB200_LANES=0 keeps calls on
+    k_synth's 8-, 16- and 32-lane variants. Both against the oracle, 5 blocks (speculative chain path), odd window count
+    per run and odd channel counts included."""
+    ch, nav = scenario.synthetic_chans(5, nchan, seed=700 + nchan)
+    ch["prn"][:, nchan // 2] = 0 if nchan > 4 else ch["prn"][:, nchan // 2]            # an idle slot in the middle
+    want, carr = scenario.oracle_run(ch, nav, ss)
+    for lanes_on, name in (("1", "k_synth_lanes"), ("0", "k_synth")):
+        monkeypatch.setenv("GPSB200_LANES", lanes_on)
+        with gps.Context(nchan, 5) as ctx:
+            ctx.set_nav_frames(nav)
+            out, cp = ctx.synth_blocks(ch, ss)
+            assert ctx.synth_kernel_name(nchan) == name
+        assert np.array_equal(out, want), name
+        assert np.array_equal(cp, carr), name
+
+
+def test_lanes_kernel_declines_code_rates_outside_its_range():
+    """f_code far from 1.023 MHz (legal for the API: <= 1.07 MHz) keeps the context on k_synth; output still exact."""
+    ch, nav = scenario.synthetic_chans(3, 8, seed=811)
+    ch["f_code"][:, 3] = 1.06e6
+    want, carr = scenario.oracle_run(ch, nav, 1)
+    with gps.Context(8, 3) as ctx:
+        ctx.set_nav_frames(nav)
+        assert ctx.synth_kernel_name(8) == "k_synth_lanes"
+        out, cp = ctx.synth_blocks(ch, 1)
+        assert ctx.synth_kernel_name(8) == "k_synth"
+    assert np.array_equal(out, want) and np.array_equal(cp, carr)

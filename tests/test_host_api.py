@@ -289,11 +289,25 @@ def test_lane_per_sample_model_is_bit_exact(nchan):
         assert counters[0] > 299000                               # nearly every sample takes the integer-only path
 
 
+def test_lane_per_sample_model_many_seeds_and_code_rates():
+    """More seeds, and code rates across the whole range the kernel accepts (1.0157 .. 1.0302 MHz): the carry-point
+    estimate (integer multiply by a 32-bit reciprocal) against the oracle."""
+    for seed in range(400, 412):
+        ok, counters = _lanes_case(12, seed)
+        assert ok, (seed, counters)
+    for i, f_code in enumerate((1.01571e6, 1.0158e6, 1.019e6, 1.0229e6, 1.0231e6, 1.027e6, 1.03019e6)):
+        ch, nav = gps.synthetic_chans(1, 6, seed=900 + i)
+        ch["f_code"][:] = f_code + np.arange(6) * 0.37
+        want, carr = scenario.oracle_run(ch, nav, 2)
+        iq, carr_out, counters = gps.lanes_model_block(ch[0], nav[0])
+        assert np.array_equal(iq, want), (f_code, counters)
+
+
 def test_lane_per_sample_model_extremes_and_forced_repairs():
     """Doppler x6 / x1e-5, phases on the wrap, NAV bit edges, idle channels; and every repair path forced on."""
     for seed, scale in ((300, 6.0), (301, 0.01), (302, 1e-5), (303, 2.5)):
         ok, counters = _lanes_case(12, seed, 0, scale, edge=True)
         assert ok, (seed, scale, counters)
-    for force in (1, 2, 3, 5, 7):
+    for force in (1, 2, 3, 5, 7, 8, 13):
         ok, counters = _lanes_case(8, 555, force, 1.0, edge=True)
         assert ok, (force, counters)
