@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 2) k_synth_lanes(SynthArgs a)
                 // Two channels per trip (an odd count is padded with the next slot, which is all zeros). The integer work is
                 // split over both integer pipes on purpose (ncu: the ALU pipe was the limiter at 81 % with the FMA pipe at 21 %):
                 // the sign bit reaches bit 31 through a multiplication by the lane's power of two.
-#pragma unroll 2
+#pragma unroll 4
                 for (int c = 0; c < nchan; c += 2) {
                     const uint4 wa = *reinterpret_cast<const uint4 *>(&wrow[c]);      // broadcast
                     const uint4 wb = *reinterpret_cast<const uint4 *>(&wrow[c + 1]);
@@ -191,32 +191,32 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 2) k_synth_lanes(SynthArgs a)
                 }
                 if (__any_sync(kFull, dmax > 0xFFFFFE00u - (lanes::kBandFast << 9))) {
                     // ---- repair: some sample of this window sits within 2^-25 cycles below an index boundary for some
-                    // channel. The whole warp redoes the window with the certain index (64-bit linear phase; exact walk
-                    // from the run anchor inside the 2^-41 band) for exactly those (channel, sample) pairs.
-                    acc0 = acc1 = acc2 = 0;
+                    // channel. Find the channel(s), take the certain index of exactly those (channel, sample) pairs (64-bit
+                    // linear phase; exact walk from the run anchor inside the 2^-41 band) and patch the sums.
                     for (int c = 0; c < nchan; c++) {
-                        const int src = hh * CH + c;
-                        const uint64_t Pc = shfl64(s.P, src), Dc = shfl64(s.D, src);
                         const uint4 wv = *reinterpret_cast<const uint4 *>(&wrow[c]);
                         const uint32_t st = sm.step[warp][c];
-                        const uint32_t sw[3] = {wv.x, wv.y, wv.z};
-                        int e[3];
+                        const uint32_t p0 = wv.w + lane3 * st, p1 = p0 + st, p2 = p1 + st;
+                        const bool risky = lanes::fast_risky(p0) | lanes::fast_risky(p1) | lanes::fast_risky(p2);
+                        if (!__any_sync(kFull, risky)) continue;
+                        const int src = hh * CH + c;
+                        const uint64_t Pc = shfl64(s.P, src), Dc = shfl64(s.D, src);
+                        if (!risky || bc[c].prn <= 0) continue;
+                        const RunCkpt k0 = a.ck[((size_t) b * a.nruns + r) * nchan + c];
+                        const lanes::Anchor ac = {k0.x, k0.y, bc[c].c_carr, bc[c].c_code, k0.nav};
+                        const uint32_t ps[3] = {p0, p1, p2}, sw[3] = {wv.x, wv.y, wv.z};
+                        int fix[3] = {0, 0, 0};
 #pragma unroll
                         for (int rr = 0; rr < 3; rr++) {
-                            const int n = (int) lane3 + rr;
-                            const uint32_t p = wv.w + (uint32_t) n * st;
-                            int k = (int) (p >> 23);
-                            if (lanes::fast_risky(p) && bc[c].prn > 0) {
-                                const RunCkpt k0 = a.ck[((size_t) b * a.nruns + r) * nchan + c];
-                                const lanes::Anchor ac = {k0.x, k0.y, bc[c].c_carr, bc[c].c_code, k0.nav};
-                                k = lanes::exact_index(Pc, Dc, ac, w + hh, n);
-                            }
-                            const int sign = (int) ((sw[rr] >> lane) & 1u);
-                            e[rr] = tab[c * 512 + ((k ^ (sign << 8)) ^ (c * SWZ))];
+                            if (!lanes::fast_risky(ps[rr])) continue;
+                            const int kf = (int) (ps[rr] >> 23);
+                            const int k = lanes::exact_index(Pc, Dc, ac, w + hh, (int) lane3 + rr);
+                            const int flip = (int) ((sw[rr] >> lane) & 1u) << 8;
+                            fix[rr] = tab[c * 512 + ((k ^ flip) ^ (c * SWZ))] - tab[c * 512 + ((kf ^ flip) ^ (c * SWZ))];
                         }
-                        acc0 += e[0];
-                        acc1 += e[1];
-                        acc2 += e[2];
+                        acc0 += fix[0];
+                        acc1 += fix[1];
+                        acc2 += fix[2];
                     }
                 }
                 // ---- quantise + pack (gps.c:2833-2845) ---------------------------------------------------------------
@@ -261,11 +261,14 @@ bool synth_lanes_applicable(const SynthArgs &a) {
 }
 
 static void lanes_shape(const SynthArgs &a, int *ctas_per_block, int *runs_per_cta) {
-    // one CTA per block when there are enough blocks to fill the GPU twice over; few blocks are split further
-    int per_block = (2 * 148 + a.nblk - 1) / a.nblk;
+    // CTAs all take about the same time and 2 x 148 of them are resident: aim at 40 or more waves so that the last,
+    // partly filled one costs little (2999 blocks as ONE CTA each are 10.1 waves -> 11: 8 % lost), in steps of one run
+    // per warp of a CTA
+    int per_block = (40 * 2 * 148 + a.nblk - 1) / a.nblk;
     if (per_block > 16) per_block = 16;
     if (per_block < 1) per_block = 1;
     int per_cta = (a.nruns + per_block - 1) / per_block;
+    per_cta = (per_cta + kLaneWarps - 1) / kLaneWarps * kLaneWarps;
     per_block = (a.nruns + per_cta - 1) / per_cta;
     *ctas_per_block = per_block;
     *runs_per_cta = per_cta;

@@ -63,6 +63,7 @@ struct ChanRun {
     uint64_t P, D;          // carrier: linear phase at the current window start, increment per sample
     uint64_t Y, E;          // code: linear phase at the current window start (chips * 2^54, < 1023 * 2^54), increment
     uint32_t inv32;         // floor(2^79 / delta3), delta3 = 3 E - 2^54 in [2^48, 2^49): the carry-point division as a multiply
+    uint32_t e22;           // E >> 22: code increment in units of 2^-32 chips (truncated)
     int iword, ibit, icode, dbit;
     bool active;
 };
@@ -91,6 +92,7 @@ GPSB_HD void init_run(ChanRun &s, bool active, double x, double y, uint32_t navp
     s.E = code_fix(d);
     const uint64_t d3 = 3 * s.E - kOne54;
     s.inv32 = active ? (uint32_t) (0x1p79 / (double) d3) : 0u;                // in (2^30, 2^31]
+    s.e22 = (uint32_t) (s.E >> 22);
     s.dbit = active ? nav_bit_at(nav, s.iword, s.ibit) : 0;
 }
 
@@ -133,9 +135,12 @@ GPSB_HD bool window_signs_fp64(const ChanRun &s, uint32_t c_lo, uint32_t c_hi, i
 // chips(w) = word w of the channel's packed, periodically extended C/A code (bit n = ca[n mod 1023]).
 // Returns false when some sample's linear code phase is too close to a chip boundary (or the carry point of a class is
 // ambiguous): the caller then builds the words with exact_signs().
-// Integer arithmetic only on the common path: the carry point t = (1 chip - F) / delta3 of a class is estimated as
-// mulhi32((2^54 - F) >> 22, inv32) = t * 2^25, short of the true value by less than 2^-23 (three truncations); when its
-// fraction keeps 2^-21 away from 0 and 1 the floor is certain and so is the band condition (band <= 2^-26).
+// 32-bit integer arithmetic only on the common path. Code phases are taken in units of 2^-32 chips (f0 = Y >> 22, e22 =
+// E >> 22): the fraction of class r, fr = f0 + r e22 (mod one chip), is short of the true one by at most 2 units, so the
+// chip offset J (its carry) is certain when fr keeps 4 units away from the wrap -- which also covers the band condition
+// of sample 0 (2^-32 chips = 1 unit). The carry point t = (1 chip - F) / delta3 is estimated from below as
+// mulhi32(2^32 - fr - 3, inv32) = t * 2^25, short by less than 2^-22 (truncations of fr, inv32 and the product); when its
+// fraction keeps 2^-21 away from 0 and 1 the floor is certain and so is the band condition of the carry point (<= 2^-26).
 template <class ChipFn, class NavFn>
 GPSB_HD bool window_signs(const ChanRun &s, ChipFn chips, NavFn nav, uint32_t S[3], bool force_fp64 = false) {
     const int j0 = (int) (s.Y >> 54);
@@ -164,18 +169,19 @@ GPSB_HD bool window_signs(const ChanRun &s, ChipFn chips, NavFn nav, uint32_t S[
             }
         }
     }
+    const uint32_t f0 = (uint32_t) (s.Y >> 22);
+    const uint32_t sh1 = funnel_r(c_lo, c_hi, 1), sh2 = funnel_r(c_lo, c_hi, 2);
     bool certain = !force_fp64;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const uint64_t phi = s.Y + (uint64_t) r * s.E;
-        const int J = (int) (phi >> 54) - j0;                                 // 0 or 1
-        const uint64_t F = phi & (kOne54 - 1);
-        const uint32_t t25 = mulhi32((uint32_t) ((kOne54 - F) >> 22), s.inv32);   // F == 0 wraps to 0: uncertain below
-        const uint32_t fl = t25 >> 25, fr = t25 & ((1u << 25) - 1u);
-        certain &= (F >> 22) != 0;                                            // F >= kBandCode
-        certain &= (fl >= 32u) | ((fr >= 16u) & (fr < (1u << 25) - 16u));
+        const uint32_t fr = f0 + (uint32_t) r * s.e22;                        // r e22 < one chip: at most one wrap
+        const bool J = fr < f0;                                               // chip offset of the class: 0 or 1
+        certain &= fr + 4u >= 8u;                                             // 4 <= fr < 2^32 - 4
+        const uint32_t t25 = mulhi32(~fr - 2u, s.inv32);
+        const uint32_t fl = t25 >> 25, frac = t25 & ((1u << 25) - 1u);
+        certain &= (fl >= 32u) | ((frac >= 16u) & (frac < (1u << 25) - 16u));
         const uint32_t lowm = fl >= 31u ? 0xFFFFFFFFu : ((2u << fl) - 1u);    // samples q < fl + 1 precede the carry
-        const uint32_t a = funnel_r(c_lo, c_hi, J), b = funnel_r(c_lo, c_hi, J + 1);
+        const uint32_t a = J ? sh1 : c_lo, b = J ? sh2 : sh1;
         S[r] = (a & lowm) | (b & ~lowm);
     }
     if (certain) return true;
