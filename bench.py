@@ -9,16 +9,16 @@ A "step" is one pass of the hot path over one batch of synthetic input: the
 899.7 Msamples) per GPU. With N ranks the stream is N x 300 s long and time-sliced:
 rank r synthesizes blocks [r*2999, (r+1)*2999) (weak scaling, no data-path collective).
 
-  value  : whole-job Msamples/s with the per-block channel parameters (and the resolved
-           block-start carrier phases) already resident in HBM; all three kernels (speculative
-           carrier probe, run checkpoints, per-sample synthesis) are inside the timed region,
-           output goes to an HBM buffer. CUDA events, max over ranks.
-  e2e    : the same metric through the blocking C-ABI call gpsb200_synth_blocks with HOST
-           buffers: start-phase guesses, H2D of the parameters, probe kernel, D2H of the probes,
-           host fix-up scan, H2D of the start phases, checkpoint + synthesis kernels and D2H of
-           the int8 stream into pinned memory are all inside the timed region.
-  roofline: k_synth against the measured HBM copy peak; algorithmic bytes = 2 B per complex
-           sample (int8 I+Q) written, nothing else counted.
+  value  : whole-job Msamples/s of the WHOLE path per step, output left in an HBM buffer: host records and
+           start-phase guesses, parameters up, carrier tables, block probes, span chaining, (N > 1: hand-over
+           of the chain state over NCCL), host scan, run checkpoints + self-check, per-sample synthesis.
+           CUDA events on the launching stream around all steps, max over ranks.
+  e2e    : the same metric through the blocking C-ABI call with HOST buffers (N = 1: gpsb200_synth_blocks;
+           N > 1: the three-step slice call): everything above plus the download of the int8/int16 stream
+           into pinned memory inside the timed region.
+  roofline: the synthesis kernel (k_synth_lanes, or k_synth when that does not apply) against the measured
+           HBM copy peak; algorithmic bytes = 2 B per complex sample (int8 I+Q) written, nothing else
+           counted.
   cpu_baseline / --impl reference: the reference's own producer loop (oracle/_ref/ref_run*,
            the unmodified gps.c behind a null sink) on this box's host cores.
 """
@@ -36,6 +36,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum (MB) of one 600-block int8 launch, by (kernel, more than 16 channels)
+NCU_DRAM_MB = {("k_synth", True): 98.34 + 303.58, ("k_synth_lanes", True): 98.39 + 319.31, ("k_synth_lanes", False): 61.84 + 317.22}
 BLOCKS_300S = 2999            # -d 300 -> round(10*300) - 1 blocks (gps.c:2703)
 SAMPLES_PER_BLOCK = 300000
 
@@ -592,6 +594,7 @@ def main():
         peak, peak_src = read_peaks()
         alg_bytes = nblk * SAMPLES_PER_BLOCK * bytes_per_sample        # one k_synth launch of this rank
         achieved = alg_bytes / (syn_ms * 1e-3) / 1e9
+        synth_kernel = ctxs[0].synth_kernel_name(nchan)
         line = {
             "metric": "IQ Msamples/s", "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
@@ -609,13 +612,14 @@ def main():
                         "k_synth_ms": round(syn_ms, 3), "host_chain_ms_per_step": round(kern["host_chain_ms"] / args.steps, 3),
                         "chain_fallback_blocks_per_step": fallbacks / args.steps,
                         "note": "kernels replayed back to back on the last step's resident state, CUDA events on the launching stream"},
-            "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": synth_kernel, "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         # ncu --set full (profiles/r2_ncu_metrics.csv): dram read+write of one 600-block int8
-                         # launch = 98.3 + 303.6 MB for 360 MB of algorithmic bytes; scaled to this launch
-                         "traffic": (int(alg_bytes * (98.34 + 303.58) / 360.0) if not args.iq16 else None),
+                         # ncu --set full (profiles/r2_ncu_metrics.csv): dram read+write of one 600-block int8 launch
+                         # (360 MB of algorithmic bytes), scaled to this launch
+                         "traffic": (int(alg_bytes * NCU_DRAM_MB.get((synth_kernel, nchan > 16), 0.0) / 360.0) or None)
+                         if not args.iq16 else None,
                          "peak_source": peak_src,
-                         "note": "path is issue-slot / shared-memory bound, not HBM bound; see DESIGN.md and profiles/"},
+                         "note": "the kernel is bound by integer issue slots and shared-memory look-ups, not by HBM; see DESIGN.md and profiles/"},
             "e2e": e2e if e2e is not None else {"value": None, "unit": "Msamples/s", "error": e2e_err or "skipped (--no-e2e)"},
         }
         if gather_ms is not None:
