@@ -26,6 +26,9 @@ gps = importlib.import_module("multi-sdr-gps-sim_b200")
 import scenario  # noqa: E402  (tests/scenario.py: oracle driver)
 
 
+kernels = {}
+
+
 def one_case(rng, case, seed):
     nchan = int(rng.choice([1, 3, 8, 12, 16, 20, 32]))
     ss = int(rng.choice([1, 2]))
@@ -37,6 +40,11 @@ def one_case(rng, case, seed):
     scale = rng.choice([1.0, 6.0, 0.01, 1e-5, 2.5, 0.3])
     ch["f_carr"] *= scale
     ch["f_code"] = 1.023e6 + ch["f_carr"] / 1540.0
+    rate = rng.random()
+    if rate < 0.2:                  # anywhere in the range k_synth_lanes accepts (its carry-point arithmetic)
+        ch["f_code"][:] = rng.uniform(1.01571e6, 1.03019e6, size=nchan)
+    elif rate < 0.25:               # outside it: the context falls back to k_synth for good
+        ch["f_code"][:, int(rng.integers(0, nchan))] = rng.choice([1.0e6, 1.04e6, 1.0155e6, 1.0303e6])
     ch["gain"] = rng.uniform(0.0, 1.2, size=ch["gain"].shape) * rng.choice([1.0, 0.02])
     edge = rng.integers(0, 4, size=nchan)
     ch["code_phase"][:, edge == 1] = np.nextafter(1023.0, 0)
@@ -50,6 +58,7 @@ def one_case(rng, case, seed):
     with gps.Context(nchan, nblk, max_nav_frames=nframes) as ctx:
         ctx.set_nav_frames(nav)
         out, cp = ctx.synth_blocks(ch, ss)
+        kernels[ctx.synth_kernel_name(nchan)] = kernels.get(ctx.synth_kernel_name(nchan), 0) + 1
     return np.array_equal(out, want) and np.array_equal(cp, carr), (case, nchan, ss, nblk, float(scale))
 
 
@@ -66,7 +75,8 @@ def main():
         if not ok:
             print("MISMATCH in differential case", what)
             return 1
-    print("differential: %d cases bit-exact vs the oracle (seed %d) in %.0f s" % (a.cases, a.seed, time.time() - t0))
+    print("differential: %d cases bit-exact vs the oracle (seed %d) in %.0f s; synthesis kernel of the cases: %s"
+          % (a.cases, a.seed, time.time() - t0, kernels))
     t0 = time.time()
     fallbacks = 0
     for k in range(a.chains):
