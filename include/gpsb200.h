@@ -198,7 +198,7 @@ int gpsb200_link_apply(const gpsb200_slice_link_t *link, int nchan, const int32_
 int gpsb200_debug_corrupt_chain(gpsb200_ctx_t *ctx, int on);
 
 /* Name of the synthesis kernel a call with nchan channels launches on this context as it stands: "k_synth_lanes"
- * (lane = sample: run length a multiple of 96, every code rate seen so far within 1.0002 .. 1.0302 MHz, 16-byte aligned
+ * (lane = sample: run length a multiple of 96 up to 2400, every code rate seen so far within 1.0157 .. 1.0302 MHz, 16-byte aligned
  * destination, GPSB200_LANES != 0) or "k_synth" (lane = channel, no such conditions). Both are bit-exact; for reporting. */
 const char *gpsb200_synth_kernel_name(const gpsb200_ctx_t *ctx, int nchan);
 

@@ -322,7 +322,7 @@ int prepare_blocks(gpsb200_ctx *ctx, const gpsb200_chan_t *chans, int b0, int b1
     });
     for (int c = 0; c < nchan; c++)
         if (status[c] != GPSB200_OK) return fail(ctx, status[c], "invalid channel parameters in slot " + std::to_string(c));
-    // k_synth_lanes covers every code rate a GPS receiver can see (1.0002 .. 1.0302 MHz); anything else keeps this
+    // k_synth_lanes covers every code rate a GPS receiver can see (1.0157 .. 1.0302 MHz); anything else keeps this
     // context on k_synth from here on (both are exact; the choice is sticky so that no launch mixes assumptions)
     for (int c = 0; c < nchan; c++)
         if (lanes_bad[c]) ctx->lanes_veto = true;

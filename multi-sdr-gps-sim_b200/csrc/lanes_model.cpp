@@ -26,7 +26,7 @@ int sine512_host(int k) {
 extern "C" int gpsb200_lanes_model_block(const gpsb200_chan_t *chans, int nchan, const uint32_t *nav /* [nchan][60] */,
                                          int run_samples, int force, int16_t *iq /* [600000] */, double *carr_out,
                                          int64_t *counters /* [4]: fast, repaired samples, slow windows, walks */) {
-    if (!chans || !nav || !iq || nchan < 1 || nchan > 32 || run_samples % lanes::kWindow != 0 ||
+    if (!chans || !nav || !iq || nchan < 1 || nchan > 32 || run_samples % lanes::kWindow != 0 || run_samples > lanes::kMaxRun ||
         GPSB200_BLOCK_SAMPLES % run_samples != 0)
         return GPSB200_ERR_ARG;
     const double delt = 1.0 / (double) GPSB200_SAMPLERATE;

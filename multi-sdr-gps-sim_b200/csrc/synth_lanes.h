@@ -1,11 +1,11 @@
-// Core of the LANE = SAMPLE synthesis (k_synth_lanes, used for calls of at most 16 channels), shared by the CUDA
-// kernel and by the host model the CPU tests compare with the oracle (gpsb200_lanes_model).
+// Core of the LANE = SAMPLE synthesis (k_synth_lanes), shared by the CUDA kernel and by the host model the CPU tests
+// compare with the oracle (gpsb200_lanes_model_block).
 //
 // Idea. The reference advances its two NCOs with one FP64 addition per sample (gps.c:2789-2826). From an EXACT
 // state at a run start (RunCkpt, written by k_checkpoints) the true phase after n steps differs from the exact LINEAR
 // phase anchor + n * increment only by the accumulated rounding: at most 2^-53 cycles per step for the carrier
 // (sums below 2 round to 2^-52, wrap subtraction exact), 2^-44 chips per step for the code (sums below 1024 round
-// to 2^-43). So over a run of n <= 2400 samples
+// to 2^-43). So over a run of n <= kMaxRun = 2400 samples (longer runs keep k_synth: the bands below are sized for this)
 //     floor(512 * carr_phase) = floor(512 * linear carrier phase)   unless the linear phase lies within
 //                               2400 * 2^-53 < 2^-41 cycles of a table-index boundary, and
 //     floor(code_phase)       = floor(linear code phase)            unless it lies within 2400 * 2^-44 < 2^-32 chips
@@ -30,6 +30,7 @@ namespace gpsb200 {
 namespace lanes {
 
 constexpr int kWindow = 96;                        // samples per window: 3 residue classes x 32
+constexpr int kMaxRun = 2400;                      // longest run the band widths below cover (n * 2^-53 < 2^-41, n * 2^-44 < 2^-32)
 constexpr uint64_t kOne54 = 1ull << 54;            // one chip in code fixed point
 constexpr uint64_t kCodeWrap54 = 1023ull << 54;    // 1023 chips
 constexpr uint64_t kBandCode = 1ull << 22;         // 2^-32 chips

@@ -303,6 +303,18 @@ def test_lane_per_sample_model_many_seeds_and_code_rates():
         assert np.array_equal(iq, want), (f_code, counters)
 
 
+def test_lane_per_sample_model_run_lengths():
+    """Every run length the kernel accepts (multiples of 96 that divide 300000, up to 2400: the band widths are sized for
+    2400 steps of accumulated rounding); longer ones are refused."""
+    ch, nav = gps.synthetic_chans(1, 7, seed=77)
+    want, carr = scenario.oracle_run(ch, nav, 2)
+    for run in (96, 480, 2400):
+        iq, carr_out, counters = gps.lanes_model_block(ch[0], nav[0], run_samples=run)
+        assert np.array_equal(iq, want), run
+    with pytest.raises(Exception):
+        gps.lanes_model_block(ch[0], nav[0], run_samples=12000)
+
+
 def test_lane_per_sample_model_extremes_and_forced_repairs():
     """Doppler x6 / x1e-5, phases on the wrap, NAV bit edges, idle channels; and every repair path forced on."""
     for seed, scale in ((300, 6.0), (301, 0.01), (302, 1e-5), (303, 2.5)):
