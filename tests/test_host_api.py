@@ -323,3 +323,31 @@ def test_lane_per_sample_model_extremes_and_forced_repairs():
     for force in (1, 2, 3, 5, 7, 8, 13):
         ok, counters = _lanes_case(8, 555, force, 1.0, edge=True)
         assert ok, (force, counters)
+
+
+def test_lane_per_sample_model_adversarial_phases():
+    """Anchors chosen so that some sample's LINEAR phase lands on a table-index boundary (carrier) or on a chip boundary
+    (code) to within an ulp: exactly where floor(linear) and floor(FP64 recurrence) may differ, i.e. where the band tests
+    have to send the sample to the exact walk. Against the oracle, and the repair counters must show the walks happened."""
+    from fractions import Fraction
+    delt = Fraction(1, 3000000)
+    walks = 0
+    rebuilt = 0
+    for case, (f_carr, n_hit, k_hit) in enumerate([(2345.678, 1000, 17), (-1843.21, 77, 300), (4999.99, 2399, 511),
+                                                   (-12.5, 150000, 256), (3.0e-3, 299999, 1), (-5999.0, 96, 0)]):
+        ch, nav = gps.synthetic_chans(1, 4, seed=60 + case)
+        # carrier of slot 0: x0 + n_hit * c == k_hit / 512 (mod 1) in exact arithmetic, then rounded to double
+        c = Fraction(float(np.float64(f_carr) * np.float64(1.0 / 3.0e6)))
+        x0 = (Fraction(k_hit, 512) - n_hit * c) % 1
+        ch["f_carr"][0, 0] = f_carr
+        ch["carr_phase"][0, 0] = min(float(x0), float(np.nextafter(1.0, 0)))
+        # code of slot 1: y0 + n_hit * d == an integer chip (mod 1023)
+        d = Fraction(float(np.float64(ch["f_code"][0, 1]) * np.float64(1.0 / 3.0e6)))
+        y0 = (Fraction(500 + case) - n_hit * d) % 1023
+        ch["code_phase"][0, 1] = float(y0)
+        want, carr = scenario.oracle_run(ch, nav, 2)
+        iq, carr_out, counters = gps.lanes_model_block(ch[0], nav[0])
+        assert np.array_equal(iq, want), (case, counters)
+        walks += int(counters[3])
+        rebuilt += int(counters[2])
+    assert walks > 0 and rebuilt > 0, (walks, rebuilt)
